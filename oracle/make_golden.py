@@ -1,0 +1,186 @@
+"""Mint the golden vectors in tests/golden/ by running the UNMODIFIED reference in the authoring container.
+
+TEST INFRASTRUCTURE ONLY.  Run as `python -m oracle.make_golden` from the repo root (needs /root/reference; about
+a minute, dominated by the reference import).  The reference ships no golden vectors for this path,
+so these files are the pin: every array below is produced by the reference's own classes
+(`ResidualVectorQuantizer`, `VectorQuantizer`, `MelResidualEncoder`'s `T.MelSpectrogram`,
+`SemanticAudioEncoder._spectral_fallback`, `AudioTokenizationPipeline`) with `use_stochastic=False` forced on every
+layer and the module in eval(), which is the argmin contract of BASELINE.json.
+
+Large codebooks are not stored: they are redrawn from the recorded torch seed in construction order
+(nat.py:2115, `torch.randn(K, D)` per layer) and checked against a stored float64 checksum.
+"""
+from __future__ import annotations
+
+import io
+import json
+import os
+import sys
+import tempfile
+import wave as wave_mod
+
+import numpy as np
+import torch
+
+from oracle.ref_shim import load_reference
+
+GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def sine_fixture(sample_rate: int = 22050, freq: float = 440.0, amp: float = 0.5) -> np.ndarray:
+    """The reference's own test tone (test_output_behavior.py:146-149), quantised to int16 like the shipped wav.
+
+    floor(x * 32768) reproduces /root/reference/test_simple.wav sample for sample (checked in main()).
+    """
+    t = np.linspace(0, 1.0, int(sample_rate * 1.0))
+    audio = np.sin(2 * np.pi * freq * t) * amp
+    return np.clip(np.floor(audio * 32768.0), -32768, 32767).astype(np.int16)
+
+
+def write_wav(path: str, pcm16: np.ndarray, sample_rate: int) -> None:
+    with wave_mod.open(path, "wb") as w:
+        w.setnchannels(1)
+        w.setsampwidth(2)
+        w.setframerate(sample_rate)
+        w.writeframes(pcm16.tobytes())
+
+
+def build_ref_rvq(nat, seed: int, D: int, K: int, L: int):
+    torch.manual_seed(seed)
+    rvq = nat.ResidualVectorQuantizer(D, K, L).eval()
+    for q in rvq.quantizers:
+        q.use_stochastic = False
+    return rvq
+
+
+def rvq_case(nat, name: str, seed: int, D: int, K: int, L: int, B: int, T: int, store_codebooks: bool,
+             x_seed: int = 1234, x_scale: float = 1.0, duplicate_rows: bool = False):
+    rvq = build_ref_rvq(nat, seed, D, K, L)
+    if duplicate_rows:                      # exact ties: rows 3 and 7 of layer 0 are identical, lower index must win
+        rvq.quantizers[0].codebook[7].copy_(rvq.quantizers[0].codebook[3])
+    g = torch.Generator().manual_seed(x_seed)
+    x = torch.randn(B, D, T, generator=g) * x_scale
+    if duplicate_rows:                      # a frame that IS a code vector: distance clamps to 0 (decode->encode)
+        x[0, :, 0] = rvq.quantizers[0].codebook[3]
+    with torch.no_grad():
+        quantized, codes, losses = rvq(x)
+        decoded = rvq.decode(codes)
+    cbs = np.stack([q.codebook.numpy() for q in rvq.quantizers])
+    out = {
+        "seed": seed, "x_seed": x_seed, "D": D, "K": K, "L": L, "B": B, "T": T, "x_scale": x_scale,
+        "duplicate_rows": int(duplicate_rows),
+        "codes": np.stack([c.numpy() for c in codes]),                            # [L, B, T] int64
+        "vq_loss": np.float32(losses["vq_loss"].item()),
+        "codebook_checksum": np.float64(cbs.astype(np.float64).sum()),
+        "x_checksum": np.float64(x.double().sum().item()),
+        "quantized_checksum": np.float64(quantized.double().sum().item()),
+        "quantized_head": quantized[:, :8, :8].numpy(),
+    }
+    if store_codebooks:                     # small cases carry every tensor; big ones are redrawn from the seeds
+        out["codebooks"] = cbs
+        out["x"] = x.numpy()
+        out["quantized"] = quantized.numpy()
+        out["decoded"] = decoded.numpy()
+    np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), **out)
+    print(f"{name}: codes[0,0,:8]={out['codes'][0, 0, :8].tolist()} vq_loss={out['vq_loss']:.6f}")
+
+
+def mel_case(nat, name: str, wave: np.ndarray, sr: int, hop: int):
+    import torchaudio.transforms as T
+    enc = nat.MelResidualEncoder(n_mels=128, n_fft=2048, hop_length=hop, target_dim=64)
+    # exactly the constructor call at nat.py:2281-2287
+    mel_t = T.MelSpectrogram(sample_rate=sr, n_fft=enc.n_fft, hop_length=enc.hop_length, n_mels=enc.n_mels,
+                             normalized=True)
+    w = torch.from_numpy(wave.astype(np.float32))[None]
+    with torch.no_grad():
+        mel = mel_t(w)
+    np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), wave=wave.astype(np.float32), sr=sr, hop=hop,
+                        n_fft=2048, n_mels=128, mel=mel.numpy(), fb=mel_t.mel_scale.fb.numpy())
+    print(f"{name}: mel {tuple(mel.shape)} max={mel.max().item():.5g}")
+
+
+def spectral_case(nat, name: str, wave: np.ndarray, sr: int):
+    enc = nat.SemanticAudioEncoder(target_dim=2)          # offline: Wav2Vec2 load fails -> spectral fallback
+    assert not enc.available
+    enc.fallback_proj = torch.nn.Linear(2, 2)
+    with torch.no_grad():
+        enc.fallback_proj.weight.copy_(torch.eye(2))
+        enc.fallback_proj.bias.zero_()
+        feats = enc._spectral_fallback(torch.from_numpy(wave.astype(np.float32))[None], sr)   # [1, 2, T]
+    np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), wave=wave.astype(np.float32), sr=sr,
+                        stats=feats[0].numpy())
+    print(f"{name}: stats {tuple(feats.shape)} first={feats[0, :, 0].tolist()}")
+
+
+def pipeline_case(nat, name: str):
+    """BASELINE.json config 1 at small dims: test tone -> full reference pipeline -> NDJSON, argmin mode."""
+    pcm = sine_fixture()
+    tmp = tempfile.mkdtemp(prefix="nat_golden_")
+    wav = os.path.join(tmp, "test_simple.wav")
+    write_wav(wav, pcm, 22050)
+    cfg = dict(semantic_dim=64, acoustic_dim=64, codebook_size=128, num_quantizers=8, n_mels=128, hop_length=512)
+    pipe = nat.AudioTokenizationPipeline(sample_rate=22050, model_config=cfg, device="cpu",
+                                         enable_reconstruction=False, deterministic=True, deterministic_seed=42,
+                                         codebook_init_method="random", enable_codebook_cache=False,
+                                         codebook_size=128)
+    tok = pipe.tokenizer
+    for rvq in (tok.semantic_quantizer, tok.acoustic_quantizer):
+        for q in rvq.quantizers:
+            q.use_stochastic = False
+    captured = {}
+    h1 = tok.semantic_quantizer.register_forward_pre_hook(lambda m, a: captured.__setitem__("sem_in", a[0].clone()))
+    h2 = tok.acoustic_quantizer.register_forward_pre_hook(lambda m, a: captured.__setitem__("ac_in", a[0].clone()))
+    old_stdout = sys.stdout
+    sys.stdout = io.StringIO()
+    try:
+        result = pipe.process_audio(wav, ndjson_streaming=True)
+    finally:
+        sys.stdout = old_stdout
+    h1.remove(); h2.remove()
+    lines = [l for l in result["ndjson_output"].splitlines() if l.strip()]
+    frames = [json.loads(l) for l in lines if '"event":"frame"' in l]
+    audio, sr = pipe.load_audio(wav)
+    with torch.no_grad():
+        mel = tok.acoustic_encoder.mel_transform(torch.from_numpy(audio).float()[None])
+    np.savez_compressed(
+        os.path.join(GOLDEN, f"{name}.npz"),
+        pcm16=pcm, audio=audio.astype(np.float32), sr=sr, mel=mel.numpy(),
+        sem_in=captured["sem_in"].numpy(), ac_in=captured["ac_in"].numpy(),
+        sem_codebooks=np.stack([q.codebook.numpy() for q in tok.semantic_quantizer.quantizers]),
+        ac_codebooks=np.stack([q.codebook.numpy() for q in tok.acoustic_quantizer.quantizers]),
+        S=np.array([f["S"] for f in frames], dtype=np.int64), A=np.array([f["A"] for f in frames], dtype=np.int64),
+        frame_lines=np.array([l for l in lines if '"event":"frame"' in l]),
+        header_line=np.array([l for l in lines if '"event":"header"' in l][:1]),
+    )
+    print(f"{name}: {len(frames)} frames, first S={frames[0]['S']} A={frames[0]['A']}")
+
+
+def main() -> None:
+    os.makedirs(GOLDEN, exist_ok=True)
+    nat = load_reference()
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    rvq_case(nat, "rvq_small", seed=7, D=64, K=128, L=4, B=1, T=50, store_codebooks=True)
+    rvq_case(nat, "rvq_ragged", seed=11, D=80, K=300, L=3, B=2, T=37, store_codebooks=True)
+    rvq_case(nat, "rvq_ties", seed=13, D=64, K=64, L=2, B=1, T=9, store_codebooks=True, duplicate_rows=True)
+    rvq_case(nat, "rvq_single_frame", seed=17, D=128, K=256, L=4, B=1, T=1, store_codebooks=True)
+    rvq_case(nat, "rvq_768x1024", seed=42, D=768, K=1024, L=4, B=1, T=1000, store_codebooks=False)
+    rvq_case(nat, "rvq_512x4096", seed=43, D=512, K=4096, L=4, B=1, T=300, store_codebooks=False)
+    rvq_case(nat, "rvq_1024x1024", seed=44, D=1024, K=1024, L=4, B=1, T=300, store_codebooks=False, x_scale=3.0)
+
+    import wave as _w
+    with _w.open(os.path.join(os.environ.get("NAT_REFERENCE_DIR", "/root/reference"), "test_simple.wav"), "rb") as f:
+        shipped = np.frombuffer(f.readframes(f.getnframes()), dtype=np.int16)
+    assert np.array_equal(shipped, sine_fixture()), "sine_fixture() no longer reproduces test_simple.wav"
+    tone = sine_fixture().astype(np.float32) / 32768.0
+    rng = np.random.default_rng(5)
+    noise = (rng.standard_normal(24000) * 0.1).astype(np.float32)
+    mel_case(nat, "mel_tone_22050_hop512", tone, 22050, 512)
+    mel_case(nat, "mel_noise_24000_hop320", noise, 24000, 320)
+    spectral_case(nat, "spectral_tone_22050", tone, 22050)
+    spectral_case(nat, "spectral_noise_24000", noise, 24000)
+    spectral_case(nat, "spectral_short", noise[:1000], 22050)         # shorter than n_fft: one zero-padded frame
+    pipeline_case(nat, "pipeline_tone_argmin")
+
+
+if __name__ == "__main__":
+    main()
