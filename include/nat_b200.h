@@ -1,0 +1,150 @@
+/*
+ * nat_b200.h -- C ABI of the B200-native RVQ + mel/spectral hot path for defcron/neural-audio-tokenizer.
+ *
+ * The reference (one Python file, cited as nat.py = /root/reference/neural_audio_tokenizer.py) has no FFI or plugin
+ * interface for this path; its boundary is a Python class surface.  Each entry point below
+ * names the reference interface it replaces.  INTEGRATION.md shows the ctypes binding a maintainer of the reference
+ * would add; `neural_audio_tokenizer_b200/_lib.py` is that binding as shipped here.
+ *
+ * Conventions
+ *   - every pointer whose name ends in _dev is a DEVICE pointer on the current CUDA device; *_host are host pointers;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is stream-ordered, no call
+ *     synchronises the device, none allocates device memory except the *_create functions;
+ *   - return value: 0 = NAT_OK, anything else is an error code; `nat_last_error()` returns a thread-local message;
+ *   - there is NO CPU implementation behind these symbols: without a CUDA device they fail with NAT_ERR_CUDA.
+ */
+#ifndef NAT_B200_H_
+#define NAT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NAT_B200_ABI_VERSION 1
+
+enum nat_status {
+    NAT_OK = 0,
+    NAT_ERR_INVALID_ARGUMENT = 1,   /* bad rank / dims / null pointer: the Python mirror raises ValueError first   */
+    NAT_ERR_CUDA = 2,               /* a CUDA runtime or driver call failed (message has the CUDA error string)     */
+    NAT_ERR_WORKSPACE = 3,          /* workspace too small for even one tile of frames                              */
+    NAT_ERR_UNSUPPORTED = 4         /* shape outside the supported envelope (D > 2048, K > 65536, n_fft != 2048 ..) */
+};
+
+/* Layout of the feature tensor handed to the quantiser. */
+enum nat_layout {
+    NAT_LAYOUT_BCT = 0,             /* [B, D, T] contiguous, time fastest: what nat.py:3239-3240 passes             */
+    NAT_LAYOUT_ROWS = 1             /* [B*T, D] contiguous, feature fastest: nat.py:2141-2142 after its transpose   */
+};
+
+/* Integer width of the emitted index streams. */
+enum nat_code_dtype {
+    NAT_CODES_I64 = 0,              /* torch.long, what nat.py:2157 / 2172 return                                    */
+    NAT_CODES_I32 = 1,
+    NAT_CODES_I16 = 2               /* K <= 32768; the width used for the multi-GPU all-gather      */
+};
+
+enum nat_rvq_flags {
+    NAT_RVQ_DEFAULT = 0,
+    NAT_RVQ_EXACT_SCAN = 1          /* skip the tensor-core pass: every frame takes the exact fp64 full scan (slow;
+                                       used by tests as an on-device cross-check and for tiny latency-bound calls)   */
+};
+
+const char* nat_last_error(void);
+int nat_abi_version(void);
+
+/* Number of SMs / name of the current device; for the bench's grid sizing report. */
+int nat_device_info(int* sm_count, int* cc_major, int* cc_minor, char* name, size_t name_len);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Residual vector quantiser (argmin contract)
+ * Replaces: ResidualVectorQuantizer.forward / .encode (nat.py:1358-1426) and the VectorQuantizer.forward it loops
+ * over (nat.py:2119-2183), argmin branch (nat.py:2155-2157).
+ * ------------------------------------------------------------------------------------------------------------- */
+
+typedef struct nat_rvq_codebooks nat_rvq_codebooks;      /* opaque: fp32 copy, scaled fp16 copy, norms, bounds  */
+
+/* Snapshot L codebooks [K, D] fp32 (the `codebook` buffers of nat.py:2115) into device-side derived state.
+ * The caller must re-create (or call nat_rvq_codebooks_update) after mutating a codebook in place
+ * (nat.py:593, 1527, 2221 all use copy_). */
+int nat_rvq_codebooks_create(const float* const* codebooks_dev, int L, int K, int D, void* stream,
+                             nat_rvq_codebooks** out);
+int nat_rvq_codebooks_update(nat_rvq_codebooks* cb, const float* const* codebooks_dev, void* stream);
+int nat_rvq_codebooks_destroy(nat_rvq_codebooks* cb);
+int nat_rvq_codebooks_dims(const nat_rvq_codebooks* cb, int* L, int* K, int* D);
+
+/* Bytes of device workspace wanted for `n_frames` frames (bounded: long inputs are processed in chunks). */
+size_t nat_rvq_workspace_bytes(const nat_rvq_codebooks* cb, int64_t n_frames);
+
+/* Per-layer counters written by nat_rvq_encode_f32 when stats_dev != NULL: uint64 [L][NAT_RVQ_STAT_FIELDS]. */
+#define NAT_RVQ_STAT_FIELDS 4
+enum nat_rvq_stat { NAT_STAT_CERTIFIED = 0,   /* frames decided by the tensor-core pass alone                  */
+                    NAT_STAT_RERANKED = 1,    /* frames whose top candidates were re-ranked exactly in fp64    */
+                    NAT_STAT_FULL_SCAN = 2,   /* frames that needed the exact full scan                        */
+                    NAT_STAT_RESERVED = 3 };
+
+/* Encode B*T frames through all L layers.
+ *   x_dev            fp32 features in `layout`
+ *   codes_out_dev    [L, B*T] integers of `code_dtype` (frame n = b*T + t); required
+ *   quantized_out_dev  optional, same layout/shape as x: sum over layers of the straight-through quantised vectors
+ *                    (nat.py:2167, 1408), bit-identical op order
+ *   loss_out_dev     optional, float [L]: per-layer q_latent + commitment_weight * e_latent (nat.py:2162-2164)
+ *   stats_dev        optional, uint64 [L][NAT_RVQ_STAT_FIELDS], ACCUMULATED (caller zeroes)
+ */
+int nat_rvq_encode_f32(const nat_rvq_codebooks* cb, const float* x_dev, int layout, int64_t B, int64_t T,
+                       void* codes_out_dev, int code_dtype, float* quantized_out_dev, float* loss_out_dev,
+                       float commitment_weight, unsigned long long* stats_dev,
+                       void* workspace_dev, size_t workspace_bytes, int flags, void* stream);
+
+/* Sum of per-layer code-vector gathers. Replaces ResidualVectorQuantizer.decode / VectorQuantizer.decode
+ * (nat.py:1428-1446, 2185-2203).  codes_dev: [n_code_layers, B*T] of `code_dtype`; only the first
+ * min(n_code_layers, L) lists are used (nat.py:1442).  out_dev: [B, D, T] (or rows) fp32. */
+int nat_rvq_decode_f32(const nat_rvq_codebooks* cb, const void* codes_dev, int code_dtype, int n_code_layers,
+                       int64_t B, int64_t T, int layout, float* out_dev, void* stream);
+
+/* Host-buffer form of nat_rvq_encode_f32 (the end-to-end call: H2D of features and D2H of indices inside).
+ * x_host / codes_out_host are host pointers (pinned memory overlaps copies with compute; pageable works). */
+int nat_rvq_encode_host_f32(const nat_rvq_codebooks* cb, const float* x_host, int layout, int64_t B, int64_t T,
+                            void* codes_out_host, int code_dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Front-end
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* Mel power spectrogram. Replaces self.mel_transform(waveform) at nat.py:2290, i.e.
+ * torchaudio.transforms.MelSpectrogram(sample_rate, n_fft, hop_length, n_mels, normalized=True) (nat.py:2281-2287):
+ * reflect-pad n_fft/2, periodic Hann, one-sided DFT, /sum(w^2), |.|^2, HTK filterbank (f_min 0, f_max sr/2, no norm).
+ *   wave_dev     [B, S] fp32, S > n_fft/2
+ *   fb_dev       optional [n_fft/2+1, n_mels] fp32 filterbank to use instead of the built-in one
+ *   mel_out_dev  [B, n_mels, 1 + S/hop] fp32
+ *   logmel_out_dev optional, same shape: 10*log10(max(mel, 1e-10)) (an addition; no tokenise-path reference)
+ * n_fft must be 2048 (the value the reference hard-codes, nat.py:2233, 2396). */
+int nat_mel_power_f32(const float* wave_dev, int64_t B, int64_t S, int sample_rate, int n_fft, int hop, int n_mels,
+                      const float* fb_dev, float* mel_out_dev, float* logmel_out_dev, void* stream);
+
+/* Spectral centroid and bandwidth per frame. Replaces the STFT loop of SemanticAudioEncoder._spectral_fallback
+ * (nat.py:2395-2433): frames = 1 + (S - n_fft)/hop (1 when S < n_fft), no centring, zero-padded tail.
+ *   wave_dev [S] fp32;  out_dev [2, T] fp32 (row 0 centroid, row 1 bandwidth). */
+int nat_spectral_stats_f32(const float* wave_dev, int64_t S, int sample_rate, int n_fft, int hop, float* out_dev,
+                           void* stream);
+
+int64_t nat_mel_num_frames(int64_t S, int hop);                       /* 1 + S/hop          (center=True)      */
+int64_t nat_spectral_num_frames(int64_t S, int n_fft, int hop);       /* nat.py:2400-2403                      */
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Debug / validation hooks (used by tests/; not part of the drop-in surface)
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* Run only the tensor-core pass of layer `layer` on rows [N, D] and dump the raw fp32 accumulators
+ * acc[n, k] = sum_d fp16(x*sx)[n,d] * fp16(c*sc)[k,d] into scores_out_dev [N, Kpad] (Kpad = K rounded up to 256),
+ * plus the per-row scale sx [N] and the layer's codebook scale sc [1]. */
+int nat_debug_rvq_scores(const nat_rvq_codebooks* cb, int layer, const float* rows_dev, int64_t N,
+                         float* scores_out_dev, float* row_scale_out_dev, float* cb_scale_out_dev,
+                         void* workspace_dev, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NAT_B200_H_ */

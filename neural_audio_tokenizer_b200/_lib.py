@@ -1,0 +1,75 @@
+"""ctypes binding of the C ABI in include/nat_b200.h (the shipped form of the stub shown in INTEGRATION.md).
+
+The library is the product: using this module without `libnat_b200.so` raises, there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libnat_b200.so")
+
+NAT_OK = 0
+LAYOUT_BCT, LAYOUT_ROWS = 0, 1
+CODES_I64, CODES_I32, CODES_I16 = 0, 1, 2
+RVQ_DEFAULT, RVQ_EXACT_SCAN = 0, 1
+STAT_FIELDS = 4
+
+# every symbol include/nat_b200.h declares: (name, restype, argtypes)
+_SIGNATURES = [
+    ("nat_last_error", c_char_p, []),
+    ("nat_abi_version", c_int, []),
+    ("nat_device_info", c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int), c_char_p, c_size_t]),
+    ("nat_rvq_codebooks_create", c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_void_p, POINTER(c_void_p)]),
+    ("nat_rvq_codebooks_update", c_int, [c_void_p, POINTER(c_void_p), c_void_p]),
+    ("nat_rvq_codebooks_destroy", c_int, [c_void_p]),
+    ("nat_rvq_codebooks_dims", c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    ("nat_rvq_workspace_bytes", c_size_t, [c_void_p, c_int64]),
+    ("nat_rvq_encode_f32", c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_int, c_void_p, c_void_p,
+                                   c_float, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    ("nat_rvq_decode_f32", c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_int64, c_int, c_void_p, c_void_p]),
+    ("nat_rvq_encode_host_f32", c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_int, c_void_p]),
+    ("nat_mel_power_f32", c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                  c_void_p, c_void_p]),
+    ("nat_spectral_stats_f32", c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
+    ("nat_mel_num_frames", c_int64, [c_int64, c_int]),
+    ("nat_spectral_num_frames", c_int64, [c_int64, c_int, c_int]),
+    ("nat_debug_rvq_scores", c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_size_t, c_void_p]),
+]
+EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]
+
+_lib = None
+
+
+class NatError(RuntimeError):
+    """A non-zero status from the native library (message from nat_last_error())."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"nat_b200 error {code}: {message}")
+        self.code = code
+
+
+def load() -> ctypes.CDLL:
+    """Load libnat_b200.so and bind every declared symbol. Raises if the library is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m neural_audio_tokenizer_b200.build` "
+            "(nvcc, sm_100a). This package has no CPU or PyTorch fallback for the RVQ / front-end path.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, restype, argtypes in _SIGNATURES:
+        fn = getattr(lib, name)            # AttributeError here means the .so is older than the header
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(status: int) -> None:
+    if status != NAT_OK:
+        raise NatError(status, (load().nat_last_error() or b"").decode("utf-8", "replace"))

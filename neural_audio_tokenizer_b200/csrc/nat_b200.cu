@@ -1,0 +1,613 @@
+// C ABI of the B200-native RVQ + front-end path (declared in include/nat_b200.h). Host-side orchestration only:
+// argument checks, workspace carving, TMA descriptors, launches on the caller's stream. No CPU compute path exists.
+#include "../../include/nat_b200.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "mel_fft.cuh"
+#include "nat_common.cuh"
+#include "rvq_gemm_sm100.cuh"
+#include "rvq_prepare.cuh"
+#include "rvq_rows.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define NAT_CUDA(expr)                                                                                        \
+    do {                                                                                                      \
+        cudaError_t e__ = (expr);                                                                             \
+        if (e__ != cudaSuccess)                                                                               \
+            return fail(NAT_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// fp16 row-major [rows, cols] -> 2-D map with a (64 x box_rows) box and 128-byte swizzle.
+int make_map_f16(CUtensorMap* map, const void* base, long long rows, long long cols, int box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (fn == nullptr) return fail(NAT_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 2};
+    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(NAT_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return NAT_OK;
+}
+
+int code_bytes(int dtype) { return dtype == NAT_CODES_I64 ? 8 : dtype == NAT_CODES_I32 ? 4 : 2; }
+
+long long chunk_cap_rows() {
+    static long long cap = [] {
+        const char* e = getenv("NAT_RVQ_CHUNK_ROWS");
+        long long v = e ? atoll(e) : 0;
+        if (v < 128) v = 1 << 19;
+        return round_up(v, 128);
+    }();
+    return cap;
+}
+
+struct Workspace {
+    float* r;
+    __half* a;
+    float4* rowinfo;
+    nat::gemm::Cand* cand;
+    double* row_loss;
+    int* scan_list;
+    int* scan_count;      // [L]
+    double* loss_acc;     // [L]
+    long long rows;       // capacity
+};
+
+constexpr size_t kWsFixed = 4096;
+
+size_t ws_per_row(int dp) { return static_cast<size_t>(dp) * 6 + 16 + 32 + 8 + 4; }
+
+bool carve(void* base, size_t bytes, int dp, long long want_rows, Workspace* ws) {
+    if (bytes <= kWsFixed + 256 * 8) return false;
+    long long rows = static_cast<long long>((bytes - kWsFixed - 256 * 8) / ws_per_row(dp));
+    rows = std::min(rows, round_up(want_rows, 128));
+    rows = rows / 128 * 128;
+    if (rows < 128) return false;
+    char* p = static_cast<char*>(base);
+    auto take = [&](size_t n) { char* q = p; p += round_up((long long)n, 256); return q; };
+    ws->scan_count = reinterpret_cast<int*>(take(kWsFixed / 2));
+    ws->loss_acc = reinterpret_cast<double*>(take(kWsFixed / 2));
+    ws->r = reinterpret_cast<float*>(take(static_cast<size_t>(rows) * dp * 4));
+    ws->a = reinterpret_cast<__half*>(take(static_cast<size_t>(rows) * dp * 2));
+    ws->rowinfo = reinterpret_cast<float4*>(take(static_cast<size_t>(rows) * 16));
+    ws->cand = reinterpret_cast<nat::gemm::Cand*>(take(static_cast<size_t>(rows) * 32));
+    ws->row_loss = reinterpret_cast<double*>(take(static_cast<size_t>(rows) * 8));
+    ws->scan_list = reinterpret_cast<int*>(take(static_cast<size_t>(rows) * 4));
+    ws->rows = rows;
+    return static_cast<size_t>(p - static_cast<char*>(base)) <= bytes;
+}
+
+}  // namespace
+
+struct nat_rvq_codebooks {
+    int L, K, D, dp, kp, device, sm_count;
+    float* cbf;                       // [L, K, dp]
+    __half* cbh;                      // [L, kp, dp]
+    float* cn32;                      // [L, kp]
+    double* cn64;                     // [L, K]
+    nat::rows::LayerConst* lc;        // [L]
+    int* scratch;                     // [L, kScratchPerLayer]
+    CUtensorMap map_b;
+    // staging arena of the host-buffer entry point (grown on first use)
+    void* host_arena_dev;
+    size_t host_arena_bytes;
+    cudaStream_t copy_stream;
+    cudaEvent_t ev[4];
+};
+
+extern "C" {
+
+const char* nat_last_error(void) { return g_last_error.c_str(); }
+int nat_abi_version(void) { return NAT_B200_ABI_VERSION; }
+
+int nat_device_info(int* sm_count, int* cc_major, int* cc_minor, char* name, size_t name_len) {
+    int dev = 0;
+    NAT_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    NAT_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    if (name && name_len) {
+        strncpy(name, prop.name, name_len - 1);
+        name[name_len - 1] = 0;
+    }
+    return NAT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- codebooks
+static int upload_codebooks(nat_rvq_codebooks* cb, const float* const* codebooks_dev, cudaStream_t st) {
+    using namespace nat;
+    NAT_CUDA(cudaMemsetAsync(cb->scratch, 0, sizeof(int) * cb->L * prepare::kScratchPerLayer, st));
+    for (int l = 0; l < cb->L; ++l) {
+        if (codebooks_dev[l] == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "codebook %d is null", l);
+        float* dst = cb->cbf + static_cast<long long>(l) * cb->K * cb->dp;
+        int* scr = cb->scratch + l * prepare::kScratchPerLayer;
+        const long long total = static_cast<long long>(cb->K) * cb->dp;
+        const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 8));
+        prepare::pack_absmax_kernel<<<grid, 256, 0, st>>>(codebooks_dev[l], cb->K, cb->D, cb->dp, dst, scr);
+        const int grid2 = std::min((cb->kp + 7) / 8, 148 * 8);
+        prepare::convert_norms_kernel<<<grid2, 256, 0, st>>>(
+            dst, cb->K, cb->kp, cb->dp, cb->cbh + static_cast<long long>(l) * cb->kp * cb->dp,
+            cb->cn32 + static_cast<long long>(l) * cb->kp, cb->cn64 + static_cast<long long>(l) * cb->K, scr);
+    }
+    prepare::finish_consts_kernel<<<1, 32, 0, st>>>(cb->scratch, cb->L, cb->lc);
+    NAT_CUDA(cudaGetLastError());
+    return NAT_OK;
+}
+
+int nat_rvq_codebooks_create(const float* const* codebooks_dev, int L, int K, int D, void* stream,
+                             nat_rvq_codebooks** out) {
+    if (out == nullptr || codebooks_dev == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    if (L < 1 || L > 16) return fail(NAT_ERR_UNSUPPORTED, "num_quantizers per stack must be in [1, 16], got %d", L);
+    if (K < 1 || K > 65536) return fail(NAT_ERR_UNSUPPORTED, "codebook_size must be in [1, 65536], got %d", K);
+    if (D < 1 || D > 2048) return fail(NAT_ERR_UNSUPPORTED, "input_dim must be in [1, 2048], got %d", D);
+    nat_rvq_codebooks* cb = new nat_rvq_codebooks();
+    memset(cb, 0, sizeof *cb);
+    cb->L = L; cb->K = K; cb->D = D;
+    cb->dp = static_cast<int>(round_up(D, 64));
+    cb->kp = static_cast<int>(round_up(K, 256));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = NAT_OK;
+    auto guard = [&](cudaError_t e, const char* what) {
+        if (e != cudaSuccess && rc == NAT_OK) rc = fail(NAT_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
+    };
+    guard(cudaGetDevice(&cb->device), "cudaGetDevice");
+    if (rc == NAT_OK) guard(cudaDeviceGetAttribute(&cb->sm_count, cudaDevAttrMultiProcessorCount, cb->device), "attr");
+    const size_t n_f = static_cast<size_t>(L) * K * cb->dp, n_h = static_cast<size_t>(L) * cb->kp * cb->dp;
+    if (rc == NAT_OK) guard(cudaMalloc(&cb->cbf, n_f * 4), "cudaMalloc(cbf)");
+    if (rc == NAT_OK) guard(cudaMalloc(&cb->cbh, n_h * 2), "cudaMalloc(cbh)");
+    if (rc == NAT_OK) guard(cudaMalloc(&cb->cn32, static_cast<size_t>(L) * cb->kp * 4), "cudaMalloc(cn32)");
+    if (rc == NAT_OK) guard(cudaMalloc(&cb->cn64, static_cast<size_t>(L) * K * 8), "cudaMalloc(cn64)");
+    if (rc == NAT_OK) guard(cudaMalloc(&cb->lc, sizeof(nat::rows::LayerConst) * L), "cudaMalloc(lc)");
+    if (rc == NAT_OK) guard(cudaMalloc(&cb->scratch, sizeof(int) * L * nat::prepare::kScratchPerLayer), "cudaMalloc");
+    if (rc == NAT_OK) guard(cudaMemsetAsync(cb->cbh, 0, n_h * 2, st), "cudaMemsetAsync(cbh)");
+    if (rc == NAT_OK) rc = upload_codebooks(cb, codebooks_dev, st);
+    if (rc == NAT_OK) rc = make_map_f16(&cb->map_b, cb->cbh, static_cast<long long>(L) * cb->kp, cb->dp, 256);
+    if (rc == NAT_OK) {
+        guard(cudaFuncSetAttribute(nat::gemm::rvq_gemm_top4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   nat::gemm::SMEM_BYTES), "cudaFuncSetAttribute");
+        guard(cudaFuncSetAttribute(nat::gemm::rvq_gemm_top4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   nat::gemm::SMEM_BYTES), "cudaFuncSetAttribute");
+    }
+    if (rc != NAT_OK) {
+        nat_rvq_codebooks_destroy(cb);
+        return rc;
+    }
+    *out = cb;
+    return NAT_OK;
+}
+
+int nat_rvq_codebooks_update(nat_rvq_codebooks* cb, const float* const* codebooks_dev, void* stream) {
+    if (cb == nullptr || codebooks_dev == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null argument");
+    return upload_codebooks(cb, codebooks_dev, static_cast<cudaStream_t>(stream));
+}
+
+int nat_rvq_codebooks_destroy(nat_rvq_codebooks* cb) {
+    if (cb == nullptr) return NAT_OK;
+    cudaFree(cb->cbf); cudaFree(cb->cbh); cudaFree(cb->cn32); cudaFree(cb->cn64); cudaFree(cb->lc);
+    cudaFree(cb->scratch); cudaFree(cb->host_arena_dev);
+    if (cb->copy_stream) cudaStreamDestroy(cb->copy_stream);
+    for (auto& e : cb->ev) if (e) cudaEventDestroy(e);
+    delete cb;
+    return NAT_OK;
+}
+
+int nat_rvq_codebooks_dims(const nat_rvq_codebooks* cb, int* L, int* K, int* D) {
+    if (cb == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null handle");
+    if (L) *L = cb->L;
+    if (K) *K = cb->K;
+    if (D) *D = cb->D;
+    return NAT_OK;
+}
+
+size_t nat_rvq_workspace_bytes(const nat_rvq_codebooks* cb, int64_t n_frames) {
+    if (cb == nullptr || n_frames <= 0) return kWsFixed + 256 * 8 + 128 * ws_per_row(64);
+    const long long rows = std::min<long long>(round_up(n_frames, 128), chunk_cap_rows());
+    return kWsFixed + 256 * 8 + static_cast<size_t>(rows) * ws_per_row(cb->dp);
+}
+
+// ------------------------------------------------------------------------------------------------- encode
+static int launch_layer0_prep(const nat_rvq_codebooks* cb, const Workspace& ws, const float* x, int layout,
+                              long long T, long long n0, int n, cudaStream_t st) {
+    using namespace nat;
+    const int warps_grid = std::min((n + 7) / 8, cb->sm_count * 16);
+    if (layout == NAT_LAYOUT_ROWS) {
+        rows::prep_rows_kernel<<<warps_grid, 256, 0, st>>>(x + n0 * cb->D, cb->D, n, cb->D, cb->dp, ws.r, ws.a,
+                                                           ws.rowinfo, cb->lc, false);
+    } else {
+        dim3 grid((n + 31) / 32, cb->dp / 32);
+        rows::bct_to_rows_kernel<<<grid, 256, 0, st>>>(x, T, cb->D, n0, n, cb->dp, ws.r);
+        rows::prep_rows_kernel<<<warps_grid, 256, 0, st>>>(nullptr, 0, n, cb->D, cb->dp, ws.r, ws.a, ws.rowinfo,
+                                                           cb->lc, true);
+    }
+    NAT_CUDA(cudaGetLastError());
+    return NAT_OK;
+}
+
+int nat_rvq_encode_f32(const nat_rvq_codebooks* cb, const float* x_dev, int layout, int64_t B, int64_t T,
+                       void* codes_out_dev, int code_dtype, float* quantized_out_dev, float* loss_out_dev,
+                       float commitment_weight, unsigned long long* stats_dev, void* workspace_dev,
+                       size_t workspace_bytes, int flags, void* stream) {
+    using namespace nat;
+    if (cb == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null codebook handle");
+    if (B < 0 || T < 0) return fail(NAT_ERR_INVALID_ARGUMENT, "negative batch or time extent");
+    if (layout != NAT_LAYOUT_BCT && layout != NAT_LAYOUT_ROWS) return fail(NAT_ERR_INVALID_ARGUMENT, "bad layout %d", layout);
+    if (code_dtype < NAT_CODES_I64 || code_dtype > NAT_CODES_I16) return fail(NAT_ERR_INVALID_ARGUMENT, "bad code dtype %d", code_dtype);
+    if (code_dtype == NAT_CODES_I16 && cb->K > 32768) return fail(NAT_ERR_INVALID_ARGUMENT, "int16 codes need codebook_size <= 32768");
+    const long long N = B * T;
+    if (N == 0) return NAT_OK;
+    if (N > (1LL << 40)) return fail(NAT_ERR_UNSUPPORTED, "too many frames");
+    if (x_dev == nullptr || codes_out_dev == nullptr || workspace_dev == nullptr)
+        return fail(NAT_ERR_INVALID_ARGUMENT, "null device pointer");
+    int dev = -1;
+    NAT_CUDA(cudaGetDevice(&dev));
+    if (dev != cb->device) return fail(NAT_ERR_INVALID_ARGUMENT, "codebooks live on device %d, current device is %d", cb->device, dev);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    Workspace ws;
+    if (!carve(workspace_dev, workspace_bytes, cb->dp, std::min<long long>(N, chunk_cap_rows()), &ws))
+        return fail(NAT_ERR_WORKSPACE, "workspace of %zu bytes cannot hold one 128-frame tile (need %zu)", workspace_bytes,
+                    nat_rvq_workspace_bytes(cb, 128));
+    CUtensorMap map_a;
+    if (int rc = make_map_f16(&map_a, ws.a, ws.rows, cb->dp, 128)) return rc;
+
+    const bool exact = (flags & NAT_RVQ_EXACT_SCAN) != 0;
+    const bool want_loss = loss_out_dev != nullptr;
+    const int cbytes = code_bytes(code_dtype);
+    const long long cb_layer_ld = static_cast<long long>(cb->K) * cb->dp;
+    NAT_CUDA(cudaMemsetAsync(ws.loss_acc, 0, sizeof(double) * cb->L, st));
+    if (cb->dp != cb->D) NAT_CUDA(cudaMemsetAsync(ws.a, 0, static_cast<size_t>(ws.rows) * cb->dp * 2, st));
+
+    for (long long n0 = 0; n0 < N; n0 += ws.rows) {
+        const int n = static_cast<int>(std::min<long long>(ws.rows, N - n0));
+        if (int rc = launch_layer0_prep(cb, ws, x_dev, layout, T, n0, n, st)) return rc;
+        NAT_CUDA(cudaMemsetAsync(ws.scan_count, 0, sizeof(int) * cb->L, st));
+        const int n_tiles = (n + gemm::BLOCK_M - 1) / gemm::BLOCK_M;
+        for (int l = 0; l < cb->L; ++l) {
+            rows::UpdateArgs ua;
+            ua.r = ws.r; ua.a = ws.a; ua.rowinfo = ws.rowinfo;
+            ua.cb = cb->cbf + l * cb_layer_ld;
+            ua.cn64 = cb->cn64 + static_cast<long long>(l) * cb->K;
+            ua.lc_next = (l + 1 < cb->L) ? cb->lc + l + 1 : nullptr;
+            ua.codes = static_cast<char*>(codes_out_dev) + (static_cast<long long>(l) * N + n0) * cbytes;
+            ua.row_loss = want_loss ? ws.row_loss : nullptr;
+            ua.stats = stats_dev ? stats_dev + l * NAT_RVQ_STAT_FIELDS : nullptr;
+            ua.n = n; ua.K = cb->K; ua.dp = cb->dp; ua.code_dtype = code_dtype;
+            const int scan_grid = cb->sm_count * 8;
+            if (!exact) {
+                gemm::rvq_gemm_top4_kernel<false><<<std::min(n_tiles, cb->sm_count), gemm::NUM_THREADS,
+                                                    gemm::SMEM_BYTES, st>>>(
+                    map_a, cb->map_b, n, n_tiles, cb->kp / gemm::BLOCK_N, cb->dp / gemm::BLOCK_K, l * cb->kp,
+                    ws.rowinfo, cb->cn32 + static_cast<long long>(l) * cb->kp, ws.cand, nullptr, 0);
+                rows::decide_update_kernel<<<std::min((n + 7) / 8, cb->sm_count * 16), 256, 0, st>>>(
+                    ua, ws.cand, ws.scan_list, ws.scan_count + l);
+                rows::full_scan_kernel<<<scan_grid, 256, 0, st>>>(ua, ws.scan_list, ws.scan_count + l, 0, false);
+            } else {
+                rows::full_scan_kernel<<<std::min(n, scan_grid), 256, 0, st>>>(ua, nullptr, nullptr, n, true);
+            }
+            if (want_loss) rows::reduce_loss_kernel<<<1, 1024, 0, st>>>(ws.row_loss, n, ws.loss_acc + l);
+            NAT_CUDA(cudaGetLastError());
+        }
+        if (quantized_out_dev != nullptr) {
+            // replay the chain from the emitted codes on a fresh copy of x (bit-identical op order, nat.py:2167/1405/1408)
+            const int warps_grid = std::min((n + 7) / 8, cb->sm_count * 16);
+            if (layout == NAT_LAYOUT_ROWS) {
+                rows::prep_rows_kernel<<<warps_grid, 256, 0, st>>>(x_dev + n0 * cb->D, cb->D, n, cb->D, cb->dp, ws.r,
+                                                                   ws.a, ws.rowinfo, cb->lc, false);
+            } else {
+                dim3 grid((n + 31) / 32, cb->dp / 32);
+                rows::bct_to_rows_kernel<<<grid, 256, 0, st>>>(x_dev, T, cb->D, n0, n, cb->dp, ws.r);
+            }
+            rows::reconstruct_rows_kernel<<<warps_grid, 256, 0, st>>>(ws.r, n, cb->dp, cb->cbf, cb_layer_ld, cb->L,
+                                                                      codes_out_dev, code_dtype, N, n0);
+            if (layout == NAT_LAYOUT_ROWS) {
+                rows::copy_rows_out_kernel<<<cb->sm_count * 8, 256, 0, st>>>(ws.r, n, cb->dp, cb->D,
+                                                                            quantized_out_dev + n0 * cb->D);
+            } else {
+                dim3 grid((n + 31) / 32, (cb->D + 31) / 32);
+                rows::rows_to_bct_kernel<<<grid, 256, 0, st>>>(ws.r, cb->dp, T, cb->D, n0, n, quantized_out_dev);
+            }
+            NAT_CUDA(cudaGetLastError());
+        }
+    }
+    if (want_loss) {
+        rows::finish_loss_kernel<<<1, 32, 0, st>>>(ws.loss_acc, cb->L, static_cast<double>(N) * cb->D,
+                                                   commitment_weight, loss_out_dev);
+        NAT_CUDA(cudaGetLastError());
+    }
+    return NAT_OK;
+}
+
+int nat_rvq_decode_f32(const nat_rvq_codebooks* cb, const void* codes_dev, int code_dtype, int n_code_layers,
+                       int64_t B, int64_t T, int layout, float* out_dev, void* stream) {
+    using namespace nat;
+    if (cb == nullptr || out_dev == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null argument");
+    if (code_dtype < NAT_CODES_I64 || code_dtype > NAT_CODES_I16) return fail(NAT_ERR_INVALID_ARGUMENT, "bad code dtype");
+    const long long N = B * T;
+    if (N <= 0) return NAT_OK;
+    const int used = std::max(0, std::min(n_code_layers, cb->L));
+    if (used > 0 && codes_dev == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null codes");
+    const long long total = N * cb->D;
+    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, cb->sm_count * 16));
+    rows::decode_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        cb->cbf, static_cast<long long>(cb->K) * cb->dp, cb->dp, cb->D, used, codes_dev, code_dtype, N, T, layout, out_dev);
+    NAT_CUDA(cudaGetLastError());
+    return NAT_OK;
+}
+
+int nat_debug_rvq_scores(const nat_rvq_codebooks* cb, int layer, const float* rows_dev, int64_t N,
+                         float* scores_out_dev, float* row_scale_out_dev, float* cb_scale_out_dev,
+                         void* workspace_dev, size_t workspace_bytes, void* stream) {
+    using namespace nat;
+    if (cb == nullptr || rows_dev == nullptr || scores_out_dev == nullptr || workspace_dev == nullptr)
+        return fail(NAT_ERR_INVALID_ARGUMENT, "null argument");
+    if (layer < 0 || layer >= cb->L) return fail(NAT_ERR_INVALID_ARGUMENT, "layer out of range");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Workspace ws;
+    if (!carve(workspace_dev, workspace_bytes, cb->dp, N, &ws) || ws.rows < N)
+        return fail(NAT_ERR_WORKSPACE, "debug call needs a workspace for all %lld rows", (long long)N);
+    CUtensorMap map_a;
+    if (int rc = make_map_f16(&map_a, ws.a, ws.rows, cb->dp, 128)) return rc;
+    const int n = static_cast<int>(N);
+    if (cb->dp != cb->D) NAT_CUDA(cudaMemsetAsync(ws.a, 0, static_cast<size_t>(ws.rows) * cb->dp * 2, st));
+    rows::prep_rows_kernel<<<std::min((n + 7) / 8, cb->sm_count * 16), 256, 0, st>>>(
+        rows_dev, cb->D, n, cb->D, cb->dp, ws.r, ws.a, ws.rowinfo, cb->lc + layer, false);
+    const int n_tiles = (n + gemm::BLOCK_M - 1) / gemm::BLOCK_M;
+    gemm::rvq_gemm_top4_kernel<true><<<std::min(n_tiles, cb->sm_count), gemm::NUM_THREADS, gemm::SMEM_BYTES, st>>>(
+        map_a, cb->map_b, n, n_tiles, cb->kp / gemm::BLOCK_N, cb->dp / gemm::BLOCK_K, layer * cb->kp, ws.rowinfo,
+        cb->cn32 + static_cast<long long>(layer) * cb->kp, ws.cand, scores_out_dev, cb->kp);
+    NAT_CUDA(cudaGetLastError());
+    if (row_scale_out_dev)
+        NAT_CUDA(cudaMemcpy2DAsync(row_scale_out_dev, 4, reinterpret_cast<const char*>(ws.rowinfo) + 12, 16, 4, n,
+                                   cudaMemcpyDeviceToDevice, st));
+    if (cb_scale_out_dev)
+        NAT_CUDA(cudaMemcpyAsync(cb_scale_out_dev, &cb->lc[layer].sc, 4, cudaMemcpyDeviceToDevice, st));
+    return NAT_OK;
+}
+
+// Host-buffer entry point: frames stream through a two-slot device arena so H2D of chunk i+1 overlaps compute of i.
+int nat_rvq_encode_host_f32(const nat_rvq_codebooks* cb_const, const float* x_host, int layout, int64_t B, int64_t T,
+                            void* codes_out_host, int code_dtype, void* stream) {
+    nat_rvq_codebooks* cb = const_cast<nat_rvq_codebooks*>(cb_const);
+    if (cb == nullptr || x_host == nullptr || codes_out_host == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null argument");
+    if (code_dtype < NAT_CODES_I64 || code_dtype > NAT_CODES_I16) return fail(NAT_ERR_INVALID_ARGUMENT, "bad code dtype");
+    const long long N = B * T;
+    if (N <= 0) return NAT_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int cbytes = code_bytes(code_dtype);
+    // slot = [x chunk | codes chunk]; plus one shared workspace
+    const long long rows = std::min<long long>(round_up(N, 128), 1 << 16);
+    const size_t x_slot = static_cast<size_t>(rows) * cb->D * 4, c_slot = static_cast<size_t>(rows) * cb->L * cbytes;
+    const size_t ws_bytes = nat_rvq_workspace_bytes(cb, rows);
+    const size_t need = 2 * (round_up(x_slot, 256) + round_up(c_slot, 256)) + ws_bytes;
+    if (cb->host_arena_bytes < need) {
+        NAT_CUDA(cudaStreamSynchronize(st));
+        if (cb->host_arena_dev) NAT_CUDA(cudaFree(cb->host_arena_dev));
+        cb->host_arena_dev = nullptr; cb->host_arena_bytes = 0;
+        NAT_CUDA(cudaMalloc(&cb->host_arena_dev, need));
+        cb->host_arena_bytes = need;
+    }
+    if (cb->copy_stream == nullptr) {
+        NAT_CUDA(cudaStreamCreateWithFlags(&cb->copy_stream, cudaStreamNonBlocking));
+        for (auto& e : cb->ev) NAT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    char* base = static_cast<char*>(cb->host_arena_dev);
+    float* xs[2]; char* cs[2];
+    for (int s = 0; s < 2; ++s) { xs[s] = reinterpret_cast<float*>(base); base += round_up(x_slot, 256);
+                                  cs[s] = base; base += round_up(c_slot, 256); }
+    void* wsp = base;
+    // The BCT layout is strided per frame range, so it is staged with a 2-D copy per batch item; rows are contiguous.
+    // copy stream: H2D(i) ; compute stream waits ev[s], encodes, D2H codes; copy stream waits ev[2+s] before reuse.
+    NAT_CUDA(cudaEventRecord(cb->ev[2], st)); NAT_CUDA(cudaEventRecord(cb->ev[3], st));
+    int slot = 0;
+    if (layout == NAT_LAYOUT_ROWS) {
+        for (long long n0 = 0; n0 < N; n0 += rows, slot ^= 1) {
+            const long long n = std::min(rows, N - n0);
+            NAT_CUDA(cudaStreamWaitEvent(cb->copy_stream, cb->ev[2 + slot], 0));
+            NAT_CUDA(cudaMemcpyAsync(xs[slot], x_host + n0 * cb->D, static_cast<size_t>(n) * cb->D * 4,
+                                     cudaMemcpyHostToDevice, cb->copy_stream));
+            NAT_CUDA(cudaEventRecord(cb->ev[slot], cb->copy_stream));
+            NAT_CUDA(cudaStreamWaitEvent(st, cb->ev[slot], 0));
+            if (int rc = nat_rvq_encode_f32(cb, xs[slot], NAT_LAYOUT_ROWS, 1, n, cs[slot], code_dtype, nullptr, nullptr,
+                                            0.25f, nullptr, wsp, ws_bytes, NAT_RVQ_DEFAULT, st)) return rc;
+            NAT_CUDA(cudaMemcpy2DAsync(static_cast<char*>(codes_out_host) + n0 * cbytes, static_cast<size_t>(N) * cbytes,
+                                       cs[slot], static_cast<size_t>(n) * cbytes, static_cast<size_t>(n) * cbytes,
+                                       cb->L, cudaMemcpyDeviceToHost, st));
+            NAT_CUDA(cudaEventRecord(cb->ev[2 + slot], st));
+        }
+    } else {
+        // chunk along time inside each batch item: x[b, :, t0:t0+n] is D rows of n floats with pitch T
+        for (long long b = 0; b < B; ++b) {
+            for (long long t0 = 0; t0 < T; t0 += rows, slot ^= 1) {
+                const long long n = std::min(rows, T - t0);
+                NAT_CUDA(cudaStreamWaitEvent(cb->copy_stream, cb->ev[2 + slot], 0));
+                NAT_CUDA(cudaMemcpy2DAsync(xs[slot], static_cast<size_t>(n) * 4, x_host + (b * cb->D) * T + t0,
+                                           static_cast<size_t>(T) * 4, static_cast<size_t>(n) * 4, cb->D,
+                                           cudaMemcpyHostToDevice, cb->copy_stream));
+                NAT_CUDA(cudaEventRecord(cb->ev[slot], cb->copy_stream));
+                NAT_CUDA(cudaStreamWaitEvent(st, cb->ev[slot], 0));
+                if (int rc = nat_rvq_encode_f32(cb, xs[slot], NAT_LAYOUT_BCT, 1, n, cs[slot], code_dtype, nullptr,
+                                                nullptr, 0.25f, nullptr, wsp, ws_bytes, NAT_RVQ_DEFAULT, st)) return rc;
+                NAT_CUDA(cudaMemcpy2DAsync(static_cast<char*>(codes_out_host) + (b * T + t0) * cbytes,
+                                           static_cast<size_t>(N) * cbytes, cs[slot], static_cast<size_t>(n) * cbytes,
+                                           static_cast<size_t>(n) * cbytes, cb->L, cudaMemcpyDeviceToHost, st));
+                NAT_CUDA(cudaEventRecord(cb->ev[2 + slot], st));
+            }
+        }
+    }
+    NAT_CUDA(cudaStreamSynchronize(st));     // host buffers are the caller's: results must have landed on return
+    return NAT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- front-end
+namespace {
+
+struct FePlan {
+    float2* tw = nullptr;        // [NFFT/2]
+    float* fbT = nullptr;        // [n_mels, NBINS] built-in HTK filterbank, band-major
+    int2* band = nullptr;
+    float* fbT_user = nullptr;   // scratch for a caller-supplied filterbank
+    int2* band_user = nullptr;
+    int sm_count = 148;
+};
+
+std::mutex g_plan_mutex;
+std::map<std::tuple<int, int, int>, FePlan> g_plans;      // (device, sample_rate, n_mels); n_mels 0 = twiddles only
+
+double hz_to_mel_htk(double f) { return 2595.0 * std::log10(1.0 + f / 700.0); }
+double mel_to_hz_htk(double m) { return 700.0 * (std::pow(10.0, m / 2595.0) - 1.0); }
+
+int get_plan(int sample_rate, int n_mels, FePlan** out) {
+    int dev = 0;
+    NAT_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_plan_mutex);
+    auto key = std::make_tuple(dev, sample_rate, n_mels);
+    auto it = g_plans.find(key);
+    if (it != g_plans.end()) { *out = &it->second; return NAT_OK; }
+    FePlan plan;
+    NAT_CUDA(cudaDeviceGetAttribute(&plan.sm_count, cudaDevAttrMultiProcessorCount, dev));
+    const int N = nat::fe::NFFT, NB = nat::fe::NBINS;
+    std::vector<float2> tw(N / 2);
+    for (int k = 0; k < N / 2; ++k) {
+        const double a = -2.0 * M_PI * k / N;
+        tw[k] = make_float2(static_cast<float>(std::cos(a)), static_cast<float>(std::sin(a)));
+    }
+    NAT_CUDA(cudaMalloc(&plan.tw, sizeof(float2) * N / 2));
+    NAT_CUDA(cudaMemcpy(plan.tw, tw.data(), sizeof(float2) * N / 2, cudaMemcpyHostToDevice));
+    if (n_mels > 0) {
+        // HTK triangles exactly as torchaudio.functional.melscale_fbanks(norm=None) defines them (f_min 0, f_max sr//2)
+        std::vector<float> fbT(static_cast<size_t>(n_mels) * NB, 0.f);
+        std::vector<int2> band(n_mels);
+        const double f_max = static_cast<double>(sample_rate / 2);
+        const double m_min = hz_to_mel_htk(0.0), m_max = hz_to_mel_htk(f_max);
+        std::vector<double> f_pts(n_mels + 2);
+        for (int i = 0; i < n_mels + 2; ++i) f_pts[i] = mel_to_hz_htk(m_min + (m_max - m_min) * i / (n_mels + 1));
+        for (int m = 0; m < n_mels; ++m) {
+            int lo = NB, hi = 0;
+            for (int k = 0; k < NB; ++k) {
+                const double f = f_max * k / (NB - 1);
+                const double down = (f - f_pts[m]) / (f_pts[m + 1] - f_pts[m]);
+                const double up = (f_pts[m + 2] - f) / (f_pts[m + 2] - f_pts[m + 1]);
+                const double v = std::max(0.0, std::min(down, up));
+                fbT[static_cast<size_t>(m) * NB + k] = static_cast<float>(v);
+                if (v > 0.0) { lo = std::min(lo, k); hi = std::max(hi, k + 1); }
+            }
+            band[m] = make_int2(std::min(lo, hi), hi);
+        }
+        NAT_CUDA(cudaMalloc(&plan.fbT, fbT.size() * 4));
+        NAT_CUDA(cudaMalloc(&plan.band, sizeof(int2) * n_mels));
+        NAT_CUDA(cudaMalloc(&plan.fbT_user, fbT.size() * 4));
+        NAT_CUDA(cudaMalloc(&plan.band_user, sizeof(int2) * n_mels));
+        NAT_CUDA(cudaMemcpy(plan.fbT, fbT.data(), fbT.size() * 4, cudaMemcpyHostToDevice));
+        NAT_CUDA(cudaMemcpy(plan.band, band.data(), sizeof(int2) * n_mels, cudaMemcpyHostToDevice));
+    }
+    auto ins = g_plans.emplace(key, plan);
+    *out = &ins.first->second;
+    return NAT_OK;
+}
+
+}  // namespace
+
+int64_t nat_mel_num_frames(int64_t S, int hop) { return hop > 0 ? 1 + S / hop : 0; }
+int64_t nat_spectral_num_frames(int64_t S, int n_fft, int hop) {
+    if (hop <= 0) return 0;
+    return S >= n_fft ? 1 + (S - n_fft) / hop : 1;
+}
+
+int nat_mel_power_f32(const float* wave_dev, int64_t B, int64_t S, int sample_rate, int n_fft, int hop, int n_mels,
+                      const float* fb_dev, float* mel_out_dev, float* logmel_out_dev, void* stream) {
+    using namespace nat;
+    if (wave_dev == nullptr || mel_out_dev == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null device pointer");
+    if (n_fft != fe::NFFT) return fail(NAT_ERR_UNSUPPORTED, "n_fft must be 2048 (the reference hard-codes it), got %d", n_fft);
+    if (hop < 1 || n_mels < 1 || n_mels > fe::MAX_MELS || sample_rate < 2) return fail(NAT_ERR_UNSUPPORTED, "unsupported hop/n_mels/sample_rate");
+    if (B < 0) return fail(NAT_ERR_INVALID_ARGUMENT, "negative batch");
+    if (B == 0) return NAT_OK;
+    if (S <= n_fft / 2) return fail(NAT_ERR_INVALID_ARGUMENT, "reflect padding needs more than n_fft/2 = %d samples, got %lld", n_fft / 2, (long long)S);
+    FePlan* plan = nullptr;
+    if (int rc = get_plan(sample_rate, n_mels, &plan)) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    fe::MelArgs p;
+    p.wave = wave_dev; p.S = S; p.T = nat_mel_num_frames(S, hop); p.hop = hop; p.n_mels = n_mels; p.tw = plan->tw;
+    p.fbT = plan->fbT; p.band = plan->band; p.mel = mel_out_dev; p.logmel = logmel_out_dev;
+    p.inv_wsum = 1.0f / (3.0f * fe::NFFT / 8.0f);                 // sum of hann^2 over a period = 3N/8
+    if (fb_dev != nullptr) {
+        fe::fb_to_banded_kernel<<<n_mels, 128, 0, st>>>(fb_dev, n_mels, plan->fbT_user, plan->band_user);
+        p.fbT = plan->fbT_user; p.band = plan->band_user;
+    }
+    const long long groups_per_clip = (p.T + fe::FRAMES_PER_CTA - 1) / fe::FRAMES_PER_CTA;
+    const long long total = groups_per_clip * B;
+    const int grid = static_cast<int>(std::min<long long>(total, plan->sm_count * 5LL * 4));
+    fe::mel_power_kernel<<<grid, fe::THREADS, 0, st>>>(p, groups_per_clip, total);
+    NAT_CUDA(cudaGetLastError());
+    return NAT_OK;
+}
+
+int nat_spectral_stats_f32(const float* wave_dev, int64_t S, int sample_rate, int n_fft, int hop, float* out_dev,
+                           void* stream) {
+    using namespace nat;
+    if (wave_dev == nullptr || out_dev == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null device pointer");
+    if (n_fft != fe::NFFT) return fail(NAT_ERR_UNSUPPORTED, "n_fft must be 2048, got %d", n_fft);
+    if (hop < 1 || S < 1 || sample_rate < 1) return fail(NAT_ERR_INVALID_ARGUMENT, "bad hop/length/sample_rate");
+    FePlan* plan = nullptr;
+    if (int rc = get_plan(sample_rate, 0, &plan)) return rc;
+    fe::SpectralArgs p;
+    p.wave = wave_dev; p.S = S; p.T = nat_spectral_num_frames(S, n_fft, hop); p.hop = hop;
+    p.bin_hz = static_cast<float>(sample_rate) / fe::NFFT; p.tw = plan->tw; p.out = out_dev;
+    const long long pairs = (p.T + 1) / 2;
+    const int grid = static_cast<int>(std::min<long long>(pairs, plan->sm_count * 5LL * 4));
+    fe::spectral_stats_kernel<<<grid, fe::THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    NAT_CUDA(cudaGetLastError());
+    return NAT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,424 @@
+// Per-frame (row) kernels of the RVQ path: operand preparation, the exact decision, the residual update, the
+// exact full-scan path, reconstruction of the quantised sum, decode, and layout transposes.
+//
+// Reference semantics restated here (nat.py = /root/reference/neural_audio_tokenizer.py):
+//   q   = codebook[j]                      nat.py:2159
+//   t   = q - r ;  q_ste = r + t           nat.py:2167   (straight-through form, kept as three fp32 ops)
+//   r'  = r - q_ste                        nat.py:1405
+//   mse = mean(t^2); loss = mse + w * mse  nat.py:2162-2164
+//   out = sum_l q_ste_l  (left to right)   nat.py:1408
+//
+// Exactness contract: the tensor-core pass yields, per frame, the four smallest packed scores. A frame
+// is decided from them only if the proven error window excludes every code that is not a candidate; candidates
+// inside the window are re-ranked with fp64 dot products on the fp32 data; frames whose fourth candidate is still
+// inside the window take the exact full scan. Ties go to the lower index, as torch.argmin does (nat.py:2157).
+#pragma once
+
+#include "nat_common.cuh"
+#include "rvq_gemm_sm100.cuh"
+
+namespace nat {
+namespace rows {
+
+// Per-layer constants derived from a codebook (device resident, written by rvq_prepare.cuh).
+struct LayerConst {
+    float sc;          // power-of-two scale applied before the fp16 cast: c_hat = c * sc
+    float chat_max;    // max_k ||c_hat_k||            (upper bound, rounded up)
+    float clo_max;     // max_k ||c_hat_k - fp16(c_hat_k)||
+    float ctil_max;    // max_k ||fp16(c_hat_k)||
+    float cmax2;       // max_k ||c_k||^2  (unscaled)
+    float pad[3];
+};
+
+constexpr float kGammaPerK = 2.384185791015625e-07f;   // 2^-22 per accumulated product: tensor-core fp32 accumulation
+
+__device__ __forceinline__ float pow2_scale_for(float amax) {
+    // sx = 2^-e with e = floor(log2(amax)), clamped so that sx stays a normal float; amax == 0 -> 1.
+    if (!(amax > 0.f)) return 1.f;
+    int e = static_cast<int>((__float_as_uint(amax) >> 23) & 0xFF) - 127;
+    e = max(-126, min(126, e));
+    return __uint_as_float(static_cast<uint32_t>(127 - e) << 23);
+}
+
+// Second half of every row producer: given the fp32 row already in global memory, emit the fp16 operand row and the
+// {alpha, bias, window} triple the coarse pass and the decision need. Warp-collective.
+__device__ __forceinline__ void finalize_row(const float4* r4, int dp4, float amax_lane,
+                                             uint2* __restrict__ a_row, float4* __restrict__ rowinfo_out,
+                                             const LayerConst* __restrict__ lc, int d_pad) {
+    const int lane = threadIdx.x & 31;
+    const float amax = warp_max(amax_lane);
+    const float sx = pow2_scale_for(amax);
+    float lo2 = 0.f, xt2 = 0.f, xh2 = 0.f;
+    for (int i = lane; i < dp4; i += 32) {
+        const float4 v = r4[i];
+        const float xs[4] = {v.x * sx, v.y * sx, v.z * sx, v.w * sx};
+        __half h[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            h[e] = __float2half_rn(xs[e]);
+            const float hf = __half2float(h[e]);
+            const float lo = xs[e] - hf;
+            lo2 = fmaf(lo, lo, lo2);
+            xt2 = fmaf(hf, hf, xt2);
+            xh2 = fmaf(xs[e], xs[e], xh2);
+        }
+        uint2 packed;
+        packed.x = static_cast<uint32_t>(__half_as_ushort(h[0])) | (static_cast<uint32_t>(__half_as_ushort(h[1])) << 16);
+        packed.y = static_cast<uint32_t>(__half_as_ushort(h[2])) | (static_cast<uint32_t>(__half_as_ushort(h[3])) << 16);
+        a_row[i] = packed;
+    }
+    lo2 = warp_sum(lo2);
+    xt2 = warp_sum(xt2);
+    xh2 = warp_sum(xh2);
+    if (lane == 0) {
+        const float up = 1.0005f;                                  // covers the fp32 rounding of the sums above
+        const float inv = 1.f / (sx * lc->sc);                     // exact: both are powers of two
+        const float rn2 = xh2 * up / (sx * sx);
+        const float xt = sqrtf(xt2 * up), lo = sqrtf(lo2 * up);
+        const float gamma = kGammaPerK * static_cast<float>(d_pad);
+        const float e_dot = lo * lc->chat_max + xt * lc->clo_max + gamma * xt * lc->ctil_max;
+        const float e_abs = 9.5367431640625e-07f * (rn2 + lc->cmax2);   // 2^-20: fp32 epilogue + ||c||^2 rounding
+        const float E = 2.f * inv * e_dot * up + e_abs + 1e-30f;
+        float4 ri;
+        ri.x = -2.f * inv;                                         // alpha: score = acc * alpha + ||c||^2 + bias
+        ri.y = (rn2 + E) * 1.001f;                                 // bias: keeps every shifted score >= 0
+        ri.z = 2.f * E;                                            // decision window
+        ri.w = sx;
+        *rowinfo_out = ri;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- layer 0 prep
+// x rows [n, D] (any alignment) -> r [n, Dp] fp32 (zero padded), A [n, Dp] fp16, rowinfo. One warp per frame.
+__global__ void __launch_bounds__(256)
+prep_rows_kernel(const float* __restrict__ x, long long x_ld, int n, int D, int dp, float* __restrict__ r,
+                 __half* __restrict__ a, float4* __restrict__ rowinfo, const LayerConst* __restrict__ lc,
+                 bool in_place) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
+        float* rr = r + static_cast<long long>(row) * dp;
+        float amax = 0.f;
+        if (in_place) {
+            const float4* r4 = reinterpret_cast<const float4*>(rr);
+            for (int i = lane; i < dp / 4; i += 32) {
+                const float4 v = r4[i];
+                amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+            }
+        } else {
+            const float* xr = x + static_cast<long long>(row) * x_ld;
+            for (int i = lane; i < dp; i += 32) {
+                const float v = i < D ? __ldg(xr + i) : 0.f;
+                rr[i] = v;
+                amax = fmaxf(amax, fabsf(v));
+            }
+            __syncwarp();
+        }
+        finalize_row(reinterpret_cast<const float4*>(rr), dp / 4, amax,
+                     reinterpret_cast<uint2*>(a + static_cast<long long>(row) * dp), rowinfo + row, lc, dp);
+    }
+}
+
+// [B, D, T] (time fastest) -> rows [n, Dp] for frames n0..n0+n of the flattened (b, t) index; and back.
+// 32 frames x 32 features per tile through shared memory so both sides are coalesced.
+__global__ void __launch_bounds__(256)
+bct_to_rows_kernel(const float* __restrict__ x, long long T, int D, long long n0, int n, int dp,
+                   float* __restrict__ r) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+    const int f0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+    for (int dy = ty; dy < 32; dy += 8) {
+        const int d = d0 + dy, f = f0 + tx;
+        float v = 0.f;
+        if (d < D && f < n) {
+            const long long g = n0 + f, b = g / T, t = g - b * T;
+            v = __ldg(x + (b * D + d) * T + t);
+        }
+        tile[dy][tx] = v;
+    }
+    __syncthreads();
+    for (int fy = ty; fy < 32; fy += 8) {
+        const int f = f0 + fy, d = d0 + tx;
+        if (f < n && d < dp) r[static_cast<long long>(f) * dp + d] = tile[tx][fy];
+    }
+}
+__global__ void __launch_bounds__(256)
+rows_to_bct_kernel(const float* __restrict__ r, int dp, long long T, int D, long long n0, int n,
+                   float* __restrict__ out) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int f0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+    for (int fy = ty; fy < 32; fy += 8) {
+        const int f = f0 + fy, d = d0 + tx;
+        tile[fy][tx] = (f < n && d < D) ? r[static_cast<long long>(f) * dp + d] : 0.f;
+    }
+    __syncthreads();
+    for (int dy = ty; dy < 32; dy += 8) {
+        const int d = d0 + dy, f = f0 + tx;
+        if (d < D && f < n) {
+            const long long g = n0 + f, b = g / T, t = g - b * T;
+            out[(b * D + d) * T + t] = tile[tx][dy];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- decision
+__device__ __forceinline__ void store_code(void* codes, int dtype, long long pos, int j) {
+    if (dtype == 0) reinterpret_cast<long long*>(codes)[pos] = j;
+    else if (dtype == 1) reinterpret_cast<int*>(codes)[pos] = j;
+    else reinterpret_cast<short*>(codes)[pos] = static_cast<short>(j);
+}
+__device__ __forceinline__ int load_code(const void* codes, int dtype, long long pos) {
+    if (dtype == 0) return static_cast<int>(reinterpret_cast<const long long*>(codes)[pos]);
+    if (dtype == 1) return reinterpret_cast<const int*>(codes)[pos];
+    return static_cast<int>(reinterpret_cast<const unsigned short*>(codes)[pos]);
+}
+
+// Exact score of code k for the fp32 row r: ||c_k||^2 - 2 r.c_k with fp64 accumulation. Warp-collective.
+__device__ __forceinline__ double exact_score(const float4* r4, const float4* __restrict__ c4, int dp4,
+                                              double cn64) {
+    const int lane = threadIdx.x & 31;
+    double acc = 0.0;
+    for (int i = lane; i < dp4; i += 32) {
+        const float4 a = r4[i];
+        const float4 b = __ldg(c4 + i);
+        acc = fma(static_cast<double>(a.x), static_cast<double>(b.x), acc);
+        acc = fma(static_cast<double>(a.y), static_cast<double>(b.y), acc);
+        acc = fma(static_cast<double>(a.z), static_cast<double>(b.z), acc);
+        acc = fma(static_cast<double>(a.w), static_cast<double>(b.w), acc);
+    }
+    acc = warp_sum(acc);
+    return cn64 - 2.0 * acc;
+}
+
+struct UpdateArgs {
+    float* r;                 // [n, Dp] residual, updated in place
+    __half* a;                // [n, Dp] fp16 operand of the NEXT layer
+    float4* rowinfo;          // per frame, read (this layer's window) then overwritten (next layer)
+    const float* cb;          // this layer's codebook [K, Dp] fp32 (zero padded)
+    const double* cn64;       // [K] ||c_k||^2 in fp64
+    const LayerConst* lc_next;   // constants of the next layer, nullptr on the last
+    void* codes;              // this layer's index stream, offset to the chunk
+    double* row_loss;         // [n] sum_d t^2 per frame, or nullptr
+    unsigned long long* stats;   // this layer's counters or nullptr
+    int n, K, dp, code_dtype;
+};
+
+// Apply code j to frame `row`: residual update in the reference's op order, loss term, next operand. Warp-collective.
+__device__ __forceinline__ void apply_code(const UpdateArgs& p, int row, int j) {
+    const int lane = threadIdx.x & 31;
+    const int dp4 = p.dp >> 2;
+    float4* r4 = reinterpret_cast<float4*>(p.r + static_cast<long long>(row) * p.dp);
+    const float4* c4 = reinterpret_cast<const float4*>(p.cb + static_cast<long long>(j) * p.dp);
+    float amax = 0.f;
+    double loss = 0.0;
+    for (int i = lane; i < dp4; i += 32) {
+        const float4 rv = r4[i];
+        const float4 cv = __ldg(c4 + i);
+        float4 nr;
+        float t, q;
+        t = __fsub_rn(cv.x, rv.x); q = __fadd_rn(rv.x, t); nr.x = __fsub_rn(rv.x, q); loss += static_cast<double>(__fmul_rn(t, t));
+        t = __fsub_rn(cv.y, rv.y); q = __fadd_rn(rv.y, t); nr.y = __fsub_rn(rv.y, q); loss += static_cast<double>(__fmul_rn(t, t));
+        t = __fsub_rn(cv.z, rv.z); q = __fadd_rn(rv.z, t); nr.z = __fsub_rn(rv.z, q); loss += static_cast<double>(__fmul_rn(t, t));
+        t = __fsub_rn(cv.w, rv.w); q = __fadd_rn(rv.w, t); nr.w = __fsub_rn(rv.w, q); loss += static_cast<double>(__fmul_rn(t, t));
+        r4[i] = nr;
+        amax = fmaxf(amax, fmaxf(fmaxf(fabsf(nr.x), fabsf(nr.y)), fmaxf(fabsf(nr.z), fabsf(nr.w))));
+    }
+    if (p.row_loss != nullptr) {
+        loss = warp_sum(loss);
+        if (lane == 0) p.row_loss[row] = loss;
+    }
+    if (lane == 0) store_code(p.codes, p.code_dtype, row, j);
+    if (p.lc_next != nullptr) {
+        __syncwarp();
+        finalize_row(r4, dp4, amax, reinterpret_cast<uint2*>(p.a + static_cast<long long>(row) * p.dp),
+                     p.rowinfo + row, p.lc_next, p.dp);
+    }
+}
+
+// One warp per frame: decide from the coarse candidates, or defer the frame to the full-scan list.
+__global__ void __launch_bounds__(256)
+decide_update_kernel(UpdateArgs p, const gemm::Cand* __restrict__ cand, int* __restrict__ scan_list,
+                     int* __restrict__ scan_count) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int dp4 = p.dp >> 2;
+    unsigned long long n_cert = 0, n_rerank = 0, n_scan = 0;
+    for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < p.n; row += warps) {
+        const gemm::Cand c = cand[row];
+        const float window = p.rowinfo[row].z;
+        const int idx[4] = {static_cast<int>(c.idx01 & 0xFFFF), static_cast<int>(c.idx01 >> 16),
+                            static_cast<int>(c.idx23 & 0xFFFF), static_cast<int>(c.idx23 >> 16)};
+        float f[4];
+        bool valid[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            f[i] = __int_as_float(c.key[i] & 0xFFFFFF00);
+            valid[i] = c.key[i] != gemm::KEY_INVALID && idx[i] < p.K && fabsf(f[i]) < 3.0e38f;
+        }
+        // 8 low bits of every key were replaced by the column: true shifted score lies in [f, f + |f| 2^-15].
+        const float thr = f[0] + fabsf(f[0]) * 6.103515625e-05f + window;
+        int nwin = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) nwin += (valid[i] && f[i] <= thr) ? 1 : 0;
+        int j = idx[0];
+        if (!valid[0] || (nwin == 4 && p.K > 4)) {
+            // the fourth candidate is still inside the window: codes we did not keep may matter -> exact full scan
+            if (lane == 0) scan_list[atomicAdd(scan_count, 1)] = row;
+            ++n_scan;
+            continue;
+        }
+        if (nwin > 1) {
+            const float4* r4 = reinterpret_cast<const float4*>(p.r + static_cast<long long>(row) * p.dp);
+            double best = 0.0;
+            int bestj = -1;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (!(valid[i] && f[i] <= thr)) continue;          // warp-uniform
+                const int k = idx[i];
+                const double s = exact_score(r4, reinterpret_cast<const float4*>(p.cb + static_cast<long long>(k) * p.dp),
+                                             dp4, p.cn64[k]);
+                if (bestj < 0 || s < best || (s == best && k < bestj)) { best = s; bestj = k; }
+            }
+            j = bestj;
+            ++n_rerank;
+        } else {
+            ++n_cert;
+        }
+        apply_code(p, row, j);
+    }
+    if (p.stats != nullptr && lane == 0) {
+        if (n_cert) atomicAdd(p.stats + 0, n_cert);
+        if (n_rerank) atomicAdd(p.stats + 1, n_rerank);
+        if (n_scan) atomicAdd(p.stats + 2, n_scan);
+    }
+}
+
+// Exact full scan, one CTA (8 warps) per listed frame; scan_list == nullptr means "every frame 0..count".
+__global__ void __launch_bounds__(256)
+full_scan_kernel(UpdateArgs p, const int* __restrict__ scan_list, const int* __restrict__ scan_count,
+                 int count_if_all, bool count_stats) {
+    __shared__ double s_best[8];
+    __shared__ int s_idx[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int dp4 = p.dp >> 2;
+    const int count = scan_list != nullptr ? *scan_count : count_if_all;
+    for (int e = blockIdx.x; e < count; e += gridDim.x) {
+        const int row = scan_list != nullptr ? scan_list[e] : e;
+        const float4* r4 = reinterpret_cast<const float4*>(p.r + static_cast<long long>(row) * p.dp);
+        double best = 0.0;
+        int bestj = -1;
+        for (int k = warp; k < p.K; k += 8) {
+            const double s = exact_score(r4, reinterpret_cast<const float4*>(p.cb + static_cast<long long>(k) * p.dp),
+                                         dp4, p.cn64[k]);
+            if (bestj < 0 || s < best) { best = s; bestj = k; }   // k ascending within a warp: first minimum kept
+        }
+        if (lane == 0) { s_best[warp] = best; s_idx[warp] = bestj; }
+        __syncthreads();
+        if (warp == 0) {
+            double b = 0.0;
+            int bj = -1;
+            for (int w = 0; w < 8; ++w) {
+                const int wj = s_idx[w];
+                if (wj < 0) continue;
+                if (bj < 0 || s_best[w] < b || (s_best[w] == b && wj < bj)) { b = s_best[w]; bj = wj; }
+            }
+            apply_code(p, row, bj);
+            if (count_stats && p.stats != nullptr && lane == 0 && scan_list == nullptr) atomicAdd(p.stats + 2, 1ULL);
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- loss
+// Deterministic fixed-order sum of row_loss[0..n) added to *acc (one block).
+__global__ void __launch_bounds__(1024)
+reduce_loss_kernel(const double* __restrict__ row_loss, int n, double* __restrict__ acc) {
+    __shared__ double sh[1024];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 1024) s += row_loss[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *acc += sh[0];
+}
+__global__ void finish_loss_kernel(const double* __restrict__ acc, int L, double count, float w,
+                                   float* __restrict__ loss_out) {
+    const int l = threadIdx.x;
+    if (l < L) {
+        const float mse = static_cast<float>(acc[l] / count);
+        loss_out[l] = __fadd_rn(mse, __fmul_rn(w, mse));           // q_latent + w * e_latent, nat.py:2164
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- outputs
+// rows [n, Dp] holding x -> rows holding sum_l q_ste_l, replaying the chain from the emitted codes. One warp/frame.
+__global__ void __launch_bounds__(256)
+reconstruct_rows_kernel(float* __restrict__ r, int n, int dp, const float* __restrict__ cb_all, long long cb_layer_ld,
+                        int L, const void* __restrict__ codes, int code_dtype, long long codes_ld,
+                        long long code_off) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int dp4 = dp >> 2;
+    for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
+        float4* r4 = reinterpret_cast<float4*>(r + static_cast<long long>(row) * dp);
+        int js[16];
+        for (int l = 0; l < L; ++l) js[l] = load_code(codes, code_dtype, l * codes_ld + code_off + row);
+        for (int i = lane; i < dp4; i += 32) {
+            float4 rv = r4[i];
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int l = 0; l < L; ++l) {
+                const float4 cv = __ldg(reinterpret_cast<const float4*>(cb_all + l * cb_layer_ld +
+                                                                         static_cast<long long>(js[l]) * dp) + i);
+                float t, q;
+                t = __fsub_rn(cv.x, rv.x); q = __fadd_rn(rv.x, t); rv.x = __fsub_rn(rv.x, q); acc.x = l ? __fadd_rn(acc.x, q) : q;
+                t = __fsub_rn(cv.y, rv.y); q = __fadd_rn(rv.y, t); rv.y = __fsub_rn(rv.y, q); acc.y = l ? __fadd_rn(acc.y, q) : q;
+                t = __fsub_rn(cv.z, rv.z); q = __fadd_rn(rv.z, t); rv.z = __fsub_rn(rv.z, q); acc.z = l ? __fadd_rn(acc.z, q) : q;
+                t = __fsub_rn(cv.w, rv.w); q = __fadd_rn(rv.w, t); rv.w = __fsub_rn(rv.w, q); acc.w = l ? __fadd_rn(acc.w, q) : q;
+            }
+            r4[i] = acc;
+        }
+    }
+}
+__global__ void __launch_bounds__(256)
+copy_rows_out_kernel(const float* __restrict__ r, int n, int dp, int D, float* __restrict__ out) {
+    const long long total = static_cast<long long>(n) * D;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long row = i / D;
+        out[i] = r[row * dp + (i - row * D)];
+    }
+}
+
+// decode: out = ((0 + cb_0[code_0]) + cb_1[code_1]) + ...   (nat.py:1438-1444). One thread per output element.
+__global__ void __launch_bounds__(256)
+decode_kernel(const float* __restrict__ cb_all, long long cb_layer_ld, int dp, int D, int L_used,
+              const void* __restrict__ codes, int code_dtype, long long N, long long T, int layout,
+              float* __restrict__ out) {
+    const long long total = N * D;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        long long n;
+        int d;
+        if (layout == 0) {          // [B, D, T]: i = (b*D + d)*T + t
+            const long long t = i % T, bd = i / T;
+            d = static_cast<int>(bd % D);
+            n = (bd / D) * T + t;
+        } else {
+            n = i / D;
+            d = static_cast<int>(i - n * D);
+        }
+        float acc = 0.f;
+        for (int l = 0; l < L_used; ++l) {
+            const int j = load_code(codes, code_dtype, l * N + n);
+            acc = __fadd_rn(acc, __ldg(cb_all + l * cb_layer_ld + static_cast<long long>(j) * dp + d));
+        }
+        out[i] = acc;
+    }
+}
+
+}  // namespace rows
+}  // namespace nat

@@ -1,0 +1,314 @@
+"""Drop-in `VectorQuantizer` / `ResidualVectorQuantizer` backed by libnat_b200.so.
+
+Mirrors the reference's Python surface for this path (nat.py = /root/reference/neural_audio_tokenizer.py):
+  * constructor signatures, attributes and buffer names   nat.py:1337-1356, 2099-2117
+  * `ResidualVectorQuantizer.forward/encode/decode`       nat.py:1358-1446
+  * `VectorQuantizer.forward/decode/_update_ema`          nat.py:2119-2221
+  * ValueError conditions for bad rank / channel count    nat.py:1378-1391, 2126-2138
+
+Contract: the native path implements the ARGMIN branch (nat.py:2155-2157). When a layer is in training mode or has
+`use_stochastic=True` the reference samples (nat.py:2150-2154); this module then calls `stochastic_delegate` if one
+was supplied and otherwise raises -- it never returns argmin codes when sampling was asked for.
+There is no CPU path: tensors must live on a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+
+
+class _CodebookPack:
+    """Owns the native `nat_rvq_codebooks` handle for a list of codebook tensors and refreshes it when any of them
+    is mutated in place (the host does `copy_` into them: nat.py:593, 1527, 2221) or moved."""
+
+    def __init__(self):
+        self.handle = None
+        self.signature = None
+        self.device = None
+
+    @staticmethod
+    def _sig(codebooks: Sequence[torch.Tensor]):
+        return tuple((cb.data_ptr(), cb._version, tuple(cb.shape), str(cb.device)) for cb in codebooks)
+
+    def get(self, codebooks: Sequence[torch.Tensor]):
+        lib = _lib.load()
+        sig = self._sig(codebooks)
+        if self.handle is not None and sig == self.signature:
+            return self.handle
+        dev = codebooks[0].device
+        K, D = codebooks[0].shape
+        for cb in codebooks:
+            if cb.device != dev or tuple(cb.shape) != (K, D) or cb.dtype != torch.float32:
+                raise ValueError("all codebooks of a stack must share device, shape [K, D] and dtype float32")
+        tensors = [cb if cb.is_contiguous() else cb.contiguous() for cb in codebooks]
+        ptrs = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        same_geometry = (self.handle is not None and self.device == dev and self.signature is not None
+                         and len(self.signature) == len(sig) and self.signature[0][2] == sig[0][2])
+        with torch.cuda.device(dev):
+            if same_geometry:
+                _lib.check(lib.nat_rvq_codebooks_update(self.handle, ptrs, stream))
+            else:
+                self.close()
+                out = ctypes.c_void_p()
+                _lib.check(lib.nat_rvq_codebooks_create(ptrs, len(tensors), K, D, stream, ctypes.byref(out)))
+                self.handle = out
+        self.signature, self.device = sig, dev
+        return self.handle
+
+    def close(self):
+        if self.handle is not None:
+            try:
+                _lib.load().nat_rvq_codebooks_destroy(self.handle)
+            except Exception:
+                pass
+            self.handle = None
+            self.signature = None
+
+    def __del__(self):
+        self.close()
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{what} is on {t.device}: the B200 RVQ path has no CPU fallback; move the module and its "
+                           "inputs to a CUDA device")
+
+
+def _native_encode(pack: _CodebookPack, codebooks: Sequence[torch.Tensor], x_bct: torch.Tensor,
+                   commitment_weight: float, want_quantized: bool, want_loss: bool, exact_scan: bool = False,
+                   stats: Optional[torch.Tensor] = None, code_dtype: torch.dtype = torch.int64):
+    """x_bct [B, C, T] fp32 CUDA -> (codes [L, B, T], quantized [B, C, T] or None, loss [L] or None)."""
+    lib = _lib.load()
+    _require_cuda(x_bct, "input")
+    if x_bct.dtype != torch.float32:
+        raise TypeError(f"expected float32 features, got {x_bct.dtype}")
+    dev = x_bct.device
+    for cb in codebooks:
+        if cb.device != dev:
+            raise RuntimeError(f"input is on {dev} but the codebook is on {cb.device}")
+    x = x_bct if x_bct.is_contiguous() else x_bct.contiguous()
+    B, C, T = x.shape
+    L = len(codebooks)
+    dt = {torch.int64: _lib.CODES_I64, torch.int32: _lib.CODES_I32, torch.int16: _lib.CODES_I16}[code_dtype]
+    codes = torch.empty((L, B, T), dtype=code_dtype, device=dev)
+    quantized = torch.empty_like(x) if want_quantized else None
+    loss = torch.empty(L, dtype=torch.float32, device=dev) if want_loss else None
+    if B * T == 0:
+        if loss is not None:
+            loss.fill_(float("nan"))           # mean over zero elements, as F.mse_loss gives
+        return codes, quantized, loss
+    with torch.cuda.device(dev):
+        handle = pack.get(codebooks)
+        ws_bytes = lib.nat_rvq_workspace_bytes(handle, B * T)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.nat_rvq_encode_f32(
+            handle, x.data_ptr(), _lib.LAYOUT_BCT, B, T, codes.data_ptr(), dt,
+            quantized.data_ptr() if quantized is not None else None,
+            loss.data_ptr() if loss is not None else None, float(commitment_weight),
+            stats.data_ptr() if stats is not None else None, ws.data_ptr(), ws_bytes,
+            _lib.RVQ_EXACT_SCAN if exact_scan else _lib.RVQ_DEFAULT,
+            torch.cuda.current_stream(dev).cuda_stream))
+        # `ws` may be freed when this frame returns: the caching allocator keeps it tied to the current stream.
+    return codes, quantized, loss
+
+
+def _native_decode(pack: _CodebookPack, codebooks: Sequence[torch.Tensor], codes: torch.Tensor, n_lists: int,
+                   B: int, T: int) -> torch.Tensor:
+    """codes [n_lists, B*T] int64 CUDA -> [B, D, T] fp32 (sum of per-layer gathers, nat.py:1438-1444)."""
+    lib = _lib.load()
+    dev = codebooks[0].device
+    _require_cuda(codebooks[0], "codebook")
+    D = codebooks[0].shape[1]
+    out = torch.empty((B, D, T), dtype=torch.float32, device=dev)
+    if B * T == 0:
+        return out
+    with torch.cuda.device(dev):
+        handle = pack.get(codebooks)
+        _lib.check(lib.nat_rvq_decode_f32(handle, codes.data_ptr() if n_lists else None, _lib.CODES_I64, n_lists, B, T,
+                                          _lib.LAYOUT_BCT, out.data_ptr(),
+                                          torch.cuda.current_stream(dev).cuda_stream))
+    return out
+
+
+class VectorQuantizer(nn.Module):
+    """One VQ layer; same constructor, buffers and return values as nat.py:2092-2221."""
+
+    def __init__(self, input_dim: int, codebook_size: int, commitment_weight: float = 0.25, ema_decay: float = 0.99,
+                 temperature: float = 0.5, use_stochastic: bool = True):
+        super().__init__()
+        self.input_dim = input_dim
+        self.codebook_size = codebook_size
+        self.commitment_weight = commitment_weight
+        self.ema_decay = ema_decay
+        self.temperature = temperature
+        self.use_stochastic = use_stochastic
+        # same draw from the global generator as nat.py:2115-2117, so seeded construction yields the same codebooks
+        self.register_buffer("codebook", torch.randn(codebook_size, input_dim))
+        self.register_buffer("ema_count", torch.zeros(codebook_size))
+        self.register_buffer("ema_weight", self.codebook.clone())
+        self.stochastic_delegate = None
+        self.exact_scan = False
+        self._pack = _CodebookPack()
+
+    def _argmin_mode(self) -> bool:
+        return not (self.training or self.use_stochastic)
+
+    def forward(self, x):
+        if x.dim() not in [2, 3]:
+            raise ValueError(f"VectorQuantizer expects 2D or 3D input, got {x.dim()}D tensor with shape {x.shape}")
+        original_shape = x.shape
+        if x.dim() == 2:
+            x = x.unsqueeze(0)
+        B, C, T = x.shape
+        if C != self.input_dim:
+            raise ValueError(f"Expected {self.input_dim} feature dimensions, got {C}")
+        if not self._argmin_mode():
+            if self.stochastic_delegate is not None:
+                return self.stochastic_delegate(x if len(original_shape) == 3 else x.squeeze(0))
+            raise NotImplementedError(
+                "VectorQuantizer is in sampling mode (training=%s, use_stochastic=%s); the B200 path implements the "
+                "argmin branch of nat.py:2155-2157 only. Set use_stochastic=False and call eval(), or supply "
+                "`stochastic_delegate`." % (self.training, self.use_stochastic))
+        codes, quantized, loss = _native_encode(self._pack, [self.codebook], x, self.commitment_weight, True, True,
+                                                exact_scan=self.exact_scan)
+        codes = codes[0]
+        loss = loss[0]
+        if len(original_shape) == 2:
+            quantized = quantized.squeeze(0)
+            codes = codes.squeeze(0)
+        return quantized, codes, loss
+
+    def decode(self, codes):
+        original_shape = codes.shape
+        if codes.dim() == 1:
+            codes = codes.unsqueeze(0)
+        B, T = codes.shape
+        flat = codes.reshape(1, -1).to(device=self.codebook.device, dtype=torch.int64).contiguous()
+        quantized = _native_decode(self._pack, [self.codebook], flat, 1, B, T)
+        if len(original_shape) == 1:
+            quantized = quantized.squeeze(0)
+        return quantized
+
+    def _update_ema(self, flat_input, codes_flat):
+        """EMA codebook update (nat.py:2205-2221); training-only, never on the tokenise path, kept in PyTorch."""
+        with torch.no_grad():
+            onehot = F.one_hot(codes_flat, self.codebook_size).float()
+            self.ema_count.mul_(self.ema_decay).add_(onehot.sum(dim=0), alpha=1 - self.ema_decay)
+            self.ema_weight.mul_(self.ema_decay).add_(torch.matmul(onehot.t(), flat_input), alpha=1 - self.ema_decay)
+            self.codebook.copy_(self.ema_weight / (self.ema_count + 1e-5).unsqueeze(1))
+
+
+class ResidualVectorQuantizer(nn.Module):
+    """L chained VQ layers; same constructor, attributes and return values as nat.py:1329-1446."""
+
+    def __init__(self, input_dim: int = 512, codebook_size: int = 4096, num_quantizers: int = 8,
+                 commitment_weight: float = 0.25, ema_decay: float = 0.99, temperature: float = 0.5,
+                 use_stochastic: bool = True):
+        super().__init__()
+        self.input_dim = input_dim
+        self.codebook_size = codebook_size
+        self.num_quantizers = num_quantizers
+        self.commitment_weight = commitment_weight
+        self.quantizers = nn.ModuleList([
+            VectorQuantizer(input_dim, codebook_size, commitment_weight, ema_decay, temperature=temperature,
+                            use_stochastic=use_stochastic)
+            for _ in range(num_quantizers)
+        ])
+        self.stochastic_delegate = None      # e.g. the reference module itself, for the sampling modes
+        self.codes_on_cpu = False            # one bulk D2H instead of per-element reads in the NDJSON emitter
+        self.exact_scan = False              # debugging aid: exact fp64 full scan for every frame
+        self.collect_stats = False
+        self.last_stats = None
+        self._pack = _CodebookPack()
+
+    # -- helpers ---------------------------------------------------------------------------------------------
+    def _codebooks(self) -> List[torch.Tensor]:
+        return [q.codebook for q in self.quantizers]
+
+    def _argmin_mode(self) -> bool:
+        return all(q._argmin_mode() if isinstance(q, VectorQuantizer) else not (q.training or q.use_stochastic)
+                   for q in self.quantizers)
+
+    def _validate(self, x):
+        if x.dim() not in [2, 3]:
+            raise ValueError(f"Expected 2D or 3D input tensor, got {x.shape}")
+        if x.dim() == 2:
+            x = x.unsqueeze(0)
+        if x.dim() != 3:
+            raise ValueError(f"Expected 3D input tensor [B, C, T], got {x.shape}")
+        if x.shape[1] != self.input_dim:
+            raise ValueError(f"Expected {self.input_dim} feature dimensions, got {x.shape[1]}")
+        return x
+
+    def _stats_tensor(self, dev):
+        if not self.collect_stats:
+            return None
+        return torch.zeros((len(self.quantizers), _lib.STAT_FIELDS), dtype=torch.int64, device=dev)
+
+    def _finish_codes(self, codes: torch.Tensor) -> List[torch.Tensor]:
+        if self.codes_on_cpu:
+            codes = codes.cpu()
+        return [codes[l] for l in range(codes.shape[0])]
+
+    # -- reference surface -----------------------------------------------------------------------------------
+    def forward(self, x, training_mode: bool = None):
+        original_training = self.training
+        if training_mode is not None:
+            self.train(training_mode)
+        try:
+            x = self._validate(x)
+            if not self._argmin_mode():
+                if self.stochastic_delegate is not None:
+                    return self.stochastic_delegate(x)
+                raise NotImplementedError(
+                    "ResidualVectorQuantizer is in sampling mode (a layer has training=True or use_stochastic=True); "
+                    "the B200 path implements the argmin contract (nat.py:2155-2157). Use "
+                    "neural_audio_tokenizer_b200.install(tokenizer, force_argmin=True), or set "
+                    "`stochastic_delegate` to the reference module.")
+            stats = self._stats_tensor(x.device)
+            codes, quantized, loss = _native_encode(self._pack, self._codebooks(), x, self.commitment_weight, True,
+                                                    True, exact_scan=self.exact_scan, stats=stats)
+            self.last_stats = stats
+            total = loss[0]
+            for l in range(1, loss.shape[0]):                # total_loss += loss, layer by layer (nat.py:1402)
+                total = total + loss[l]
+            losses = {"vq_loss": total, "num_layers": len(self.quantizers)}
+            return quantized, self._finish_codes(codes), losses
+        finally:
+            if training_mode is not None:
+                self.train(original_training)
+
+    def encode(self, x):
+        """Codes only (nat.py:1422-1426): skips the quantised sum and the losses the reference computes and drops."""
+        with torch.no_grad():
+            original_training = self.training
+            self.train(False)
+            try:
+                x = self._validate(x)
+                if not self._argmin_mode():
+                    if self.stochastic_delegate is not None:
+                        return self.stochastic_delegate.encode(x)
+                    raise NotImplementedError("encode(): a layer has use_stochastic=True; see forward()")
+                stats = self._stats_tensor(x.device)
+                codes, _, _ = _native_encode(self._pack, self._codebooks(), x, self.commitment_weight, False, False,
+                                             exact_scan=self.exact_scan, stats=stats)
+                self.last_stats = stats
+                return self._finish_codes(codes)
+            finally:
+                self.train(original_training)
+
+    def decode(self, codes):
+        if not codes:
+            return torch.zeros(1, self.input_dim, 1)
+        B, T = codes[0].shape
+        dev = self.quantizers[0].codebook.device
+        used = codes[:len(self.quantizers)]
+        stacked = torch.stack([c.reshape(-1).to(device=dev, dtype=torch.int64) for c in used]).contiguous()
+        return _native_decode(self._pack, self._codebooks(), stacked, len(used), B, T)

@@ -1,0 +1,82 @@
+"""Parity of the CUDA front-end (mel power, spectral centroid/bandwidth) against golden vectors and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import mel_oracle
+
+pytestmark = pytest.mark.gpu
+
+# Stated fp32 tolerances (see tests/test_oracle_golden.py for where they come from):
+#   mel, our torch-built filterbank (bit-identical to torchaudio's): 2e-5 * max(mel) + 1e-7 per clip
+#   mel, library's built-in double-precision filterbank:             1e-4 * max(mel) + 1e-6 per clip
+#   centroid / bandwidth: rtol 2e-4, atol 1e-2 Hz
+MEL_TOL_FB, MEL_TOL_BUILTIN = 2e-5, 1e-4
+
+
+@pytest.mark.parametrize("name", ["mel_tone_22050_hop512", "mel_noise_24000_hop320"])
+def test_mel_matches_torchaudio_golden(name):
+    from neural_audio_tokenizer_b200 import MelSpectrogram, _lib
+    g = load_golden(name)
+    sr, hop = int(g["sr"]), int(g["hop"])
+    wave = torch.from_numpy(g["wave"]).cuda()
+    ref = g["mel"]                                                    # [1, 128, T]
+    mt = MelSpectrogram(sample_rate=sr, n_fft=2048, hop_length=hop, n_mels=128, normalized=True, log_mel=True).cuda()
+    assert mt.sample_rate == sr
+    np.testing.assert_array_equal(mt.fb.cpu().numpy(), g["fb"])       # same filterbank as the reference multiplies by
+    mel = mt(wave[None])
+    assert mel.shape == ref.shape
+    err = np.abs(mel.cpu().numpy() - ref).max()
+    assert err <= MEL_TOL_FB * ref.max() + 1e-7, err
+    assert mt(wave).shape == ref.shape[1:]                            # 1-D input keeps torchaudio's shape rule
+    np.testing.assert_allclose(mt.last_log_mel.cpu().numpy(), mel_oracle.log_mel_db(mel.cpu().numpy())[0],
+                               rtol=0, atol=2e-4)
+    # built-in filterbank of the C ABI (fb_dev = NULL)
+    lib = _lib.load()
+    out = torch.empty_like(mel)
+    _lib.check(lib.nat_mel_power_f32(wave.data_ptr(), 1, wave.numel(), sr, 2048, hop, 128, None, out.data_ptr(), None,
+                                     None))
+    torch.cuda.synchronize()
+    assert np.abs(out.cpu().numpy() - ref).max() <= MEL_TOL_BUILTIN * ref.max() + 1e-6
+
+
+def test_mel_batch_and_long_clip_vs_oracle():
+    from neural_audio_tokenizer_b200 import MelSpectrogram
+    rng = np.random.default_rng(9)
+    wave = (rng.standard_normal((3, 24000 * 4 + 123)) * 0.1).astype(np.float32)
+    mt = MelSpectrogram(sample_rate=24000, n_fft=2048, hop_length=320, n_mels=128).cuda()
+    mel = mt(torch.from_numpy(wave).cuda()).cpu().numpy()
+    fb = mt.fb.cpu().numpy().astype(np.float64)
+    for b in range(3):
+        ref = (mel_oracle.stft_power(wave[b], 2048, 320).T @ fb).T
+        assert mel[b].shape == ref.shape == (128, 1 + wave.shape[1] // 320)
+        assert np.abs(mel[b] - ref).max() <= MEL_TOL_FB * ref.max() + 1e-7
+
+
+@pytest.mark.parametrize("name", ["spectral_tone_22050", "spectral_noise_24000", "spectral_short"])
+def test_spectral_stats_match_reference_golden(name):
+    from neural_audio_tokenizer_b200 import spectral_stats
+    g = load_golden(name)
+    st = spectral_stats(torch.from_numpy(g["wave"]).cuda()[None], int(g["sr"]))
+    assert st.shape == g["stats"].shape
+    np.testing.assert_allclose(st.cpu().numpy(), g["stats"], rtol=2e-4, atol=1e-2)
+
+
+def test_pipeline_fixture_mel():
+    from neural_audio_tokenizer_b200 import MelSpectrogram
+    g = load_golden("pipeline_tone_argmin")
+    mt = MelSpectrogram(sample_rate=int(g["sr"]), n_fft=2048, hop_length=512, n_mels=128).cuda()
+    mel = mt(torch.from_numpy(g["audio"]).cuda()[None]).cpu().numpy()
+    assert np.abs(mel - g["mel"]).max() <= MEL_TOL_FB * g["mel"].max() + 1e-7
+
+
+def test_frontend_errors():
+    from neural_audio_tokenizer_b200 import MelSpectrogram
+    with pytest.raises(ValueError):
+        MelSpectrogram(sample_rate=22050, n_fft=1024)
+    mt = MelSpectrogram(sample_rate=22050, n_fft=2048, hop_length=512).cuda()
+    with pytest.raises(RuntimeError):
+        mt(torch.zeros(1, 1000, device="cuda"))                       # shorter than the reflect pad
+    with pytest.raises(RuntimeError):
+        mt(torch.zeros(1, 4096))                                      # CPU tensor: no fallback
