@@ -1,0 +1,15 @@
+"""B200-native drop-in for the RVQ and mel/spectral hot path of defcron/neural-audio-tokenizer.
+
+Host-side mirror of the reference's Python surface for this path:
+`ResidualVectorQuantizer`, `VectorQuantizer`, `MelSpectrogram`, `spectral_stats`, plus `install()` to graft them
+into a live reference tokenizer. All arithmetic happens in `libnat_b200.so` (hand-written sm_100a CUDA behind the
+C ABI of include/nat_b200.h); there is no CPU or PyTorch-op fallback.
+"""
+from .frontend import MelSpectrogram, spectral_stats
+from .install import install, patch_reference_module
+from .quantizers import ResidualVectorQuantizer, VectorQuantizer
+from .sharding import all_gather_codes, shard_range
+
+__all__ = ["ResidualVectorQuantizer", "VectorQuantizer", "MelSpectrogram", "spectral_stats", "install",
+           "patch_reference_module", "all_gather_codes", "shard_range"]
+__version__ = "0.1.0"
