@@ -98,6 +98,26 @@ int nat_rvq_encode_f32(const nat_rvq_codebooks* cb, const float* x_dev, int layo
                        float commitment_weight, unsigned long long* stats_dev,
                        void* workspace_dev, size_t workspace_bytes, int flags, void* stream);
 
+/* Same call, timed: CUDA events around every kernel launch on `stream`, then a stream synchronise, and the summed
+ * device milliseconds per kernel class in prof_ms_host[NAT_PROF_FIELDS] (bench.py's roofline leg; not a hot path). */
+#define NAT_PROF_FIELDS 8
+enum nat_prof { NAT_PROF_PREP = 0,        /* layout transpose + fp16 operand / bound preparation of layer 0        */
+                NAT_PROF_GEMM = 1,        /* tcgen05 distance GEMM + top-4 epilogue (the dominant kernel)           */
+                NAT_PROF_DECIDE = 2,      /* exact decision + residual update + next-layer operand                  */
+                NAT_PROF_SCAN = 3,        /* exact full-scan path                                                   */
+                NAT_PROF_LOSS = 4,
+                NAT_PROF_OUTPUT = 5,      /* quantised-sum reconstruction / layout out                              */
+                NAT_PROF_GEMM_LAUNCHES = 6, /* count, not ms                                                        */
+                NAT_PROF_WALL = 7 };      /* first event to last event                                              */
+int nat_rvq_encode_profile_f32(const nat_rvq_codebooks* cb, const float* x_dev, int layout, int64_t B, int64_t T,
+                               void* codes_out_dev, int code_dtype, float* quantized_out_dev, float* loss_out_dev,
+                               float commitment_weight, unsigned long long* stats_dev,
+                               void* workspace_dev, size_t workspace_bytes, int flags, void* stream,
+                               float* prof_ms_host);
+
+/* Kernel launches issued by this library in this process so far (bench.py's gpu_launches). */
+unsigned long long nat_launch_count(void);
+
 /* Sum of per-layer code-vector gathers. Replaces ResidualVectorQuantizer.decode / VectorQuantizer.decode
  * (nat.py:1428-1446, 2185-2203).  codes_dev: [n_code_layers, B*T] of `code_dtype`; only the first
  * min(n_code_layers, L) lists are used (nat.py:1442).  out_dev: [B, D, T] (or rows) fp32. */

@@ -16,6 +16,8 @@ LAYOUT_BCT, LAYOUT_ROWS = 0, 1
 CODES_I64, CODES_I32, CODES_I16 = 0, 1, 2
 RVQ_DEFAULT, RVQ_EXACT_SCAN = 0, 1
 STAT_FIELDS = 4
+PROF_FIELDS = 8
+PROF_NAMES = ("prep", "gemm", "decide_update", "full_scan", "loss", "output", "gemm_launches", "wall")
 
 # every symbol include/nat_b200.h declares: (name, restype, argtypes)
 _SIGNATURES = [
@@ -29,6 +31,10 @@ _SIGNATURES = [
     ("nat_rvq_workspace_bytes", c_size_t, [c_void_p, c_int64]),
     ("nat_rvq_encode_f32", c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_int, c_void_p, c_void_p,
                                    c_float, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    ("nat_rvq_encode_profile_f32", c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_int, c_void_p,
+                                           c_void_p, c_float, c_void_p, c_void_p, c_size_t, c_int, c_void_p,
+                                           POINTER(c_float)]),
+    ("nat_launch_count", ctypes.c_ulonglong, []),
     ("nat_rvq_decode_f32", c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     ("nat_rvq_encode_host_f32", c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_int, c_void_p]),
     ("nat_mel_power_f32", c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p,

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -45,6 +46,32 @@ int fail(int code, const char* fmt, ...) {
     } while (0)
 
 inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
+
+std::atomic<unsigned long long> g_launches{0};
+
+// Optional per-kernel-class timing (nat_rvq_encode_profile_f32): CUDA events around every launch, on its stream.
+struct Profiler {
+    struct Span { int cls; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+};
+thread_local Profiler* g_prof = nullptr;
+
+struct LaunchScope {
+    cudaStream_t st;
+    cudaEvent_t b = nullptr;
+    LaunchScope(int cls, cudaStream_t s) : st(s) {
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (g_prof != nullptr) {
+            cudaEvent_t a;
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            cudaEventRecord(a, st);
+            g_prof->spans.push_back({cls, a, b});
+        }
+    }
+    ~LaunchScope() { if (b != nullptr) cudaEventRecord(b, st); }
+};
+#define NAT_LAUNCH(cls, st, ...) do { LaunchScope scope__((cls), (st)); __VA_ARGS__; } while (0)
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -173,13 +200,13 @@ static int upload_codebooks(nat_rvq_codebooks* cb, const float* const* codebooks
         int* scr = cb->scratch + l * prepare::kScratchPerLayer;
         const long long total = static_cast<long long>(cb->K) * cb->dp;
         const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 8));
-        prepare::pack_absmax_kernel<<<grid, 256, 0, st>>>(codebooks_dev[l], cb->K, cb->D, cb->dp, dst, scr);
+        NAT_LAUNCH(6, st, prepare::pack_absmax_kernel<<<grid, 256, 0, st>>>(codebooks_dev[l], cb->K, cb->D, cb->dp, dst, scr));
         const int grid2 = std::min((cb->kp + 7) / 8, 148 * 8);
-        prepare::convert_norms_kernel<<<grid2, 256, 0, st>>>(
+        NAT_LAUNCH(6, st, prepare::convert_norms_kernel<<<grid2, 256, 0, st>>>(
             dst, cb->K, cb->kp, cb->dp, cb->cbh + static_cast<long long>(l) * cb->kp * cb->dp,
-            cb->cn32 + static_cast<long long>(l) * cb->kp, cb->cn64 + static_cast<long long>(l) * cb->K, scr);
+            cb->cn32 + static_cast<long long>(l) * cb->kp, cb->cn64 + static_cast<long long>(l) * cb->K, scr));
     }
-    prepare::finish_consts_kernel<<<1, 32, 0, st>>>(cb->scratch, cb->L, cb->lc);
+    NAT_LAUNCH(6, st, prepare::finish_consts_kernel<<<1, 32, 0, st>>>(cb->scratch, cb->L, cb->lc));
     NAT_CUDA(cudaGetLastError());
     return NAT_OK;
 }
@@ -262,13 +289,13 @@ static int launch_layer0_prep(const nat_rvq_codebooks* cb, const Workspace& ws, 
     using namespace nat;
     const int warps_grid = std::min((n + 7) / 8, cb->sm_count * 16);
     if (layout == NAT_LAYOUT_ROWS) {
-        rows::prep_rows_kernel<<<warps_grid, 256, 0, st>>>(x + n0 * cb->D, cb->D, n, cb->D, cb->dp, ws.r, ws.a,
-                                                           ws.rowinfo, cb->lc, false);
+        NAT_LAUNCH(0, st, rows::prep_rows_kernel<<<warps_grid, 256, 0, st>>>(x + n0 * cb->D, cb->D, n, cb->D, cb->dp, ws.r, ws.a,
+                                                           ws.rowinfo, cb->lc, false));
     } else {
         dim3 grid((n + 31) / 32, cb->dp / 32);
-        rows::bct_to_rows_kernel<<<grid, 256, 0, st>>>(x, T, cb->D, n0, n, cb->dp, ws.r);
-        rows::prep_rows_kernel<<<warps_grid, 256, 0, st>>>(nullptr, 0, n, cb->D, cb->dp, ws.r, ws.a, ws.rowinfo,
-                                                           cb->lc, true);
+        NAT_LAUNCH(0, st, rows::bct_to_rows_kernel<<<grid, 256, 0, st>>>(x, T, cb->D, n0, n, cb->dp, ws.r));
+        NAT_LAUNCH(0, st, rows::prep_rows_kernel<<<warps_grid, 256, 0, st>>>(nullptr, 0, n, cb->D, cb->dp, ws.r, ws.a, ws.rowinfo,
+                                                           cb->lc, true));
     }
     NAT_CUDA(cudaGetLastError());
     return NAT_OK;
@@ -325,48 +352,76 @@ int nat_rvq_encode_f32(const nat_rvq_codebooks* cb, const float* x_dev, int layo
             ua.n = n; ua.K = cb->K; ua.dp = cb->dp; ua.code_dtype = code_dtype;
             const int scan_grid = cb->sm_count * 8;
             if (!exact) {
-                gemm::rvq_gemm_top4_kernel<false><<<std::min(n_tiles, cb->sm_count), gemm::NUM_THREADS,
+                NAT_LAUNCH(1, st, gemm::rvq_gemm_top4_kernel<false><<<std::min(n_tiles, cb->sm_count), gemm::NUM_THREADS,
                                                     gemm::SMEM_BYTES, st>>>(
                     map_a, cb->map_b, n, n_tiles, cb->kp / gemm::BLOCK_N, cb->dp / gemm::BLOCK_K, l * cb->kp,
-                    ws.rowinfo, cb->cn32 + static_cast<long long>(l) * cb->kp, ws.cand, nullptr, 0);
-                rows::decide_update_kernel<<<std::min((n + 7) / 8, cb->sm_count * 16), 256, 0, st>>>(
-                    ua, ws.cand, ws.scan_list, ws.scan_count + l);
-                rows::full_scan_kernel<<<scan_grid, 256, 0, st>>>(ua, ws.scan_list, ws.scan_count + l, 0, false);
+                    ws.rowinfo, cb->cn32 + static_cast<long long>(l) * cb->kp, ws.cand, nullptr, 0));
+                NAT_LAUNCH(2, st, rows::decide_update_kernel<<<std::min((n + 7) / 8, cb->sm_count * 16), 256, 0, st>>>(
+                    ua, ws.cand, ws.scan_list, ws.scan_count + l));
+                NAT_LAUNCH(3, st, rows::full_scan_kernel<<<scan_grid, 256, 0, st>>>(ua, ws.scan_list, ws.scan_count + l, 0, false));
             } else {
-                rows::full_scan_kernel<<<std::min(n, scan_grid), 256, 0, st>>>(ua, nullptr, nullptr, n, true);
+                NAT_LAUNCH(3, st, rows::full_scan_kernel<<<std::min(n, scan_grid), 256, 0, st>>>(ua, nullptr, nullptr, n, true));
             }
-            if (want_loss) rows::reduce_loss_kernel<<<1, 1024, 0, st>>>(ws.row_loss, n, ws.loss_acc + l);
+            if (want_loss) NAT_LAUNCH(4, st, rows::reduce_loss_kernel<<<1, 1024, 0, st>>>(ws.row_loss, n, ws.loss_acc + l));
             NAT_CUDA(cudaGetLastError());
         }
         if (quantized_out_dev != nullptr) {
             // replay the chain from the emitted codes on a fresh copy of x (bit-identical op order, nat.py:2167/1405/1408)
             const int warps_grid = std::min((n + 7) / 8, cb->sm_count * 16);
             if (layout == NAT_LAYOUT_ROWS) {
-                rows::prep_rows_kernel<<<warps_grid, 256, 0, st>>>(x_dev + n0 * cb->D, cb->D, n, cb->D, cb->dp, ws.r,
-                                                                   ws.a, ws.rowinfo, cb->lc, false);
+                NAT_LAUNCH(0, st, rows::prep_rows_kernel<<<warps_grid, 256, 0, st>>>(x_dev + n0 * cb->D, cb->D, n, cb->D, cb->dp, ws.r,
+                                                                   ws.a, ws.rowinfo, cb->lc, false));
             } else {
                 dim3 grid((n + 31) / 32, cb->dp / 32);
-                rows::bct_to_rows_kernel<<<grid, 256, 0, st>>>(x_dev, T, cb->D, n0, n, cb->dp, ws.r);
+                NAT_LAUNCH(0, st, rows::bct_to_rows_kernel<<<grid, 256, 0, st>>>(x_dev, T, cb->D, n0, n, cb->dp, ws.r));
             }
-            rows::reconstruct_rows_kernel<<<warps_grid, 256, 0, st>>>(ws.r, n, cb->dp, cb->cbf, cb_layer_ld, cb->L,
-                                                                      codes_out_dev, code_dtype, N, n0);
+            NAT_LAUNCH(5, st, rows::reconstruct_rows_kernel<<<warps_grid, 256, 0, st>>>(ws.r, n, cb->dp, cb->cbf, cb_layer_ld, cb->L,
+                                                                      codes_out_dev, code_dtype, N, n0));
             if (layout == NAT_LAYOUT_ROWS) {
-                rows::copy_rows_out_kernel<<<cb->sm_count * 8, 256, 0, st>>>(ws.r, n, cb->dp, cb->D,
-                                                                            quantized_out_dev + n0 * cb->D);
+                NAT_LAUNCH(5, st, rows::copy_rows_out_kernel<<<cb->sm_count * 8, 256, 0, st>>>(ws.r, n, cb->dp, cb->D,
+                                                                            quantized_out_dev + n0 * cb->D));
             } else {
                 dim3 grid((n + 31) / 32, (cb->D + 31) / 32);
-                rows::rows_to_bct_kernel<<<grid, 256, 0, st>>>(ws.r, cb->dp, T, cb->D, n0, n, quantized_out_dev);
+                NAT_LAUNCH(5, st, rows::rows_to_bct_kernel<<<grid, 256, 0, st>>>(ws.r, cb->dp, T, cb->D, n0, n, quantized_out_dev));
             }
             NAT_CUDA(cudaGetLastError());
         }
     }
     if (want_loss) {
-        rows::finish_loss_kernel<<<1, 32, 0, st>>>(ws.loss_acc, cb->L, static_cast<double>(N) * cb->D,
-                                                   commitment_weight, loss_out_dev);
+        NAT_LAUNCH(4, st, rows::finish_loss_kernel<<<1, 32, 0, st>>>(ws.loss_acc, cb->L, static_cast<double>(N) * cb->D,
+                                                   commitment_weight, loss_out_dev));
         NAT_CUDA(cudaGetLastError());
     }
     return NAT_OK;
 }
+
+int nat_rvq_encode_profile_f32(const nat_rvq_codebooks* cb, const float* x_dev, int layout, int64_t B, int64_t T,
+                               void* codes_out_dev, int code_dtype, float* quantized_out_dev, float* loss_out_dev,
+                               float commitment_weight, unsigned long long* stats_dev, void* workspace_dev,
+                               size_t workspace_bytes, int flags, void* stream, float* prof_ms_host) {
+    if (prof_ms_host == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null profile buffer");
+    Profiler prof;
+    g_prof = &prof;
+    const int rc = nat_rvq_encode_f32(cb, x_dev, layout, B, T, codes_out_dev, code_dtype, quantized_out_dev,
+                                      loss_out_dev, commitment_weight, stats_dev, workspace_dev, workspace_bytes, flags,
+                                      stream);
+    g_prof = nullptr;
+    cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+    for (int i = 0; i < NAT_PROF_FIELDS; ++i) prof_ms_host[i] = 0.f;
+    for (auto& sp : prof.spans) {
+        float ms = 0.f;
+        if (e == cudaSuccess && cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess && sp.cls < 6) prof_ms_host[sp.cls] += ms;
+        if (sp.cls == NAT_PROF_GEMM) prof_ms_host[NAT_PROF_GEMM_LAUNCHES] += 1.f;
+    }
+    if (e == cudaSuccess && !prof.spans.empty())
+        cudaEventElapsedTime(&prof_ms_host[NAT_PROF_WALL], prof.spans.front().a, prof.spans.back().b);
+    for (auto& sp : prof.spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    if (rc != NAT_OK) return rc;
+    if (e != cudaSuccess) return fail(NAT_ERR_CUDA, "cudaStreamSynchronize failed: %s", cudaGetErrorString(e));
+    return NAT_OK;
+}
+
+unsigned long long nat_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int nat_rvq_decode_f32(const nat_rvq_codebooks* cb, const void* codes_dev, int code_dtype, int n_code_layers,
                        int64_t B, int64_t T, int layout, float* out_dev, void* stream) {
@@ -379,8 +434,8 @@ int nat_rvq_decode_f32(const nat_rvq_codebooks* cb, const void* codes_dev, int c
     if (used > 0 && codes_dev == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null codes");
     const long long total = N * cb->D;
     const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, cb->sm_count * 16));
-    rows::decode_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        cb->cbf, static_cast<long long>(cb->K) * cb->dp, cb->dp, cb->D, used, codes_dev, code_dtype, N, T, layout, out_dev);
+    NAT_LAUNCH(5, static_cast<cudaStream_t>(stream), rows::decode_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        cb->cbf, static_cast<long long>(cb->K) * cb->dp, cb->dp, cb->D, used, codes_dev, code_dtype, N, T, layout, out_dev));
     NAT_CUDA(cudaGetLastError());
     return NAT_OK;
 }
@@ -400,12 +455,12 @@ int nat_debug_rvq_scores(const nat_rvq_codebooks* cb, int layer, const float* ro
     if (int rc = make_map_f16(&map_a, ws.a, ws.rows, cb->dp, 128)) return rc;
     const int n = static_cast<int>(N);
     if (cb->dp != cb->D) NAT_CUDA(cudaMemsetAsync(ws.a, 0, static_cast<size_t>(ws.rows) * cb->dp * 2, st));
-    rows::prep_rows_kernel<<<std::min((n + 7) / 8, cb->sm_count * 16), 256, 0, st>>>(
-        rows_dev, cb->D, n, cb->D, cb->dp, ws.r, ws.a, ws.rowinfo, cb->lc + layer, false);
+    NAT_LAUNCH(0, st, rows::prep_rows_kernel<<<std::min((n + 7) / 8, cb->sm_count * 16), 256, 0, st>>>(
+        rows_dev, cb->D, n, cb->D, cb->dp, ws.r, ws.a, ws.rowinfo, cb->lc + layer, false));
     const int n_tiles = (n + gemm::BLOCK_M - 1) / gemm::BLOCK_M;
-    gemm::rvq_gemm_top4_kernel<true><<<std::min(n_tiles, cb->sm_count), gemm::NUM_THREADS, gemm::SMEM_BYTES, st>>>(
+    NAT_LAUNCH(1, st, gemm::rvq_gemm_top4_kernel<true><<<std::min(n_tiles, cb->sm_count), gemm::NUM_THREADS, gemm::SMEM_BYTES, st>>>(
         map_a, cb->map_b, n, n_tiles, cb->kp / gemm::BLOCK_N, cb->dp / gemm::BLOCK_K, layer * cb->kp, ws.rowinfo,
-        cb->cn32 + static_cast<long long>(layer) * cb->kp, ws.cand, scores_out_dev, cb->kp);
+        cb->cn32 + static_cast<long long>(layer) * cb->kp, ws.cand, scores_out_dev, cb->kp));
     NAT_CUDA(cudaGetLastError());
     if (row_scale_out_dev)
         NAT_CUDA(cudaMemcpy2DAsync(row_scale_out_dev, 4, reinterpret_cast<const char*>(ws.rowinfo) + 12, 16, 4, n,
@@ -581,13 +636,13 @@ int nat_mel_power_f32(const float* wave_dev, int64_t B, int64_t S, int sample_ra
     p.fbT = plan->fbT; p.band = plan->band; p.mel = mel_out_dev; p.logmel = logmel_out_dev;
     p.inv_wsum = 1.0f / (3.0f * fe::NFFT / 8.0f);                 // sum of hann^2 over a period = 3N/8
     if (fb_dev != nullptr) {
-        fe::fb_to_banded_kernel<<<n_mels, 128, 0, st>>>(fb_dev, n_mels, plan->fbT_user, plan->band_user);
+        NAT_LAUNCH(7, st, fe::fb_to_banded_kernel<<<n_mels, 128, 0, st>>>(fb_dev, n_mels, plan->fbT_user, plan->band_user));
         p.fbT = plan->fbT_user; p.band = plan->band_user;
     }
     const long long groups_per_clip = (p.T + fe::FRAMES_PER_CTA - 1) / fe::FRAMES_PER_CTA;
     const long long total = groups_per_clip * B;
     const int grid = static_cast<int>(std::min<long long>(total, plan->sm_count * 5LL * 4));
-    fe::mel_power_kernel<<<grid, fe::THREADS, 0, st>>>(p, groups_per_clip, total);
+    NAT_LAUNCH(7, st, fe::mel_power_kernel<<<grid, fe::THREADS, 0, st>>>(p, groups_per_clip, total));
     NAT_CUDA(cudaGetLastError());
     return NAT_OK;
 }
@@ -605,7 +660,7 @@ int nat_spectral_stats_f32(const float* wave_dev, int64_t S, int sample_rate, in
     p.bin_hz = static_cast<float>(sample_rate) / fe::NFFT; p.tw = plan->tw; p.out = out_dev;
     const long long pairs = (p.T + 1) / 2;
     const int grid = static_cast<int>(std::min<long long>(pairs, plan->sm_count * 5LL * 4));
-    fe::spectral_stats_kernel<<<grid, fe::THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    NAT_LAUNCH(7, static_cast<cudaStream_t>(stream), fe::spectral_stats_kernel<<<grid, fe::THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p));
     NAT_CUDA(cudaGetLastError());
     return NAT_OK;
 }
