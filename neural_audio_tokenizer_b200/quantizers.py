@@ -304,6 +304,36 @@ class ResidualVectorQuantizer(nn.Module):
             finally:
                 self.train(original_training)
 
+    def encode_host(self, x_cpu: torch.Tensor, code_dtype: torch.dtype = torch.int16,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """End-to-end form of encode(): HOST features [B, C, T] in, HOST index streams [L, B, T] out.
+
+        One native call (nat_rvq_encode_host_f32) streams the frames through a two-slot device arena so the H2D copy
+        of chunk i+1 overlaps the kernels of chunk i, and brings the int16 codes back. Pinned inputs/outputs make the
+        copies asynchronous; pageable memory works too. The module's codebooks must be on a CUDA device."""
+        lib = _lib.load()
+        if x_cpu.is_cuda:
+            raise ValueError("encode_host() takes host tensors; use encode() for device tensors")
+        x = self._validate(x_cpu)
+        if x.dtype != torch.float32:
+            raise TypeError(f"expected float32 features, got {x.dtype}")
+        if not self._argmin_mode():
+            raise NotImplementedError("encode_host(): a layer is in sampling mode; see forward()")
+        x = x if x.is_contiguous() else x.contiguous()
+        B, C, T = x.shape
+        L = len(self.quantizers)
+        dev = self.quantizers[0].codebook.device
+        _require_cuda(self.quantizers[0].codebook, "codebook")
+        dt = {torch.int64: _lib.CODES_I64, torch.int32: _lib.CODES_I32, torch.int16: _lib.CODES_I16}[code_dtype]
+        if out is None:
+            out = torch.empty((L, B, T), dtype=code_dtype, pin_memory=True)
+        if B * T:
+            with torch.cuda.device(dev):
+                handle = self._pack.get(self._codebooks())
+                _lib.check(lib.nat_rvq_encode_host_f32(handle, x.data_ptr(), _lib.LAYOUT_BCT, B, T, out.data_ptr(), dt,
+                                                       torch.cuda.current_stream(dev).cuda_stream))
+        return out
+
     def decode(self, codes):
         if not codes:
             return torch.zeros(1, self.input_dim, 1)
