@@ -245,6 +245,8 @@ int nat_rvq_codebooks_create(const float* const* codebooks_dev, int L, int K, in
                                    nat::gemm::SMEM_BYTES), "cudaFuncSetAttribute");
         guard(cudaFuncSetAttribute(nat::gemm::rvq_gemm_top4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    nat::gemm::SMEM_BYTES), "cudaFuncSetAttribute");
+        guard(cudaFuncSetAttribute(nat::rows::prep_bct_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   200 * 1024), "cudaFuncSetAttribute");
     }
     if (rc != NAT_OK) {
         nat_rvq_codebooks_destroy(cb);
@@ -292,10 +294,16 @@ static int launch_layer0_prep(const nat_rvq_codebooks* cb, const Workspace& ws, 
         NAT_LAUNCH(0, st, rows::prep_rows_kernel<<<warps_grid, 256, 0, st>>>(x + n0 * cb->D, cb->D, n, cb->D, cb->dp, ws.r, ws.a,
                                                            ws.rowinfo, cb->lc, false));
     } else {
-        dim3 grid((n + 31) / 32, cb->dp / 32);
-        NAT_LAUNCH(0, st, rows::bct_to_rows_kernel<<<grid, 256, 0, st>>>(x, T, cb->D, n0, n, cb->dp, ws.r));
-        NAT_LAUNCH(0, st, rows::prep_rows_kernel<<<warps_grid, 256, 0, st>>>(nullptr, 0, n, cb->D, cb->dp, ws.r, ws.a, ws.rowinfo,
-                                                           cb->lc, true));
+        const size_t smem = static_cast<size_t>(rows::kPrepFrames) * (cb->dp + 1) * sizeof(float);
+        if (smem <= 200 * 1024) {
+            NAT_LAUNCH(0, st, rows::prep_bct_fused_kernel<<<(n + rows::kPrepFrames - 1) / rows::kPrepFrames, 256, smem, st>>>(
+                x, T, cb->D, n0, n, cb->dp, ws.r, ws.a, ws.rowinfo, cb->lc));
+        } else {
+            dim3 grid((n + 31) / 32, cb->dp / 32);
+            NAT_LAUNCH(0, st, rows::bct_to_rows_kernel<<<grid, 256, 0, st>>>(x, T, cb->D, n0, n, cb->dp, ws.r));
+            NAT_LAUNCH(0, st, rows::prep_rows_kernel<<<warps_grid, 256, 0, st>>>(nullptr, 0, n, cb->D, cb->dp, ws.r, ws.a,
+                                                                              ws.rowinfo, cb->lc, true));
+        }
     }
     NAT_CUDA(cudaGetLastError());
     return NAT_OK;
@@ -350,7 +358,8 @@ int nat_rvq_encode_f32(const nat_rvq_codebooks* cb, const float* x_dev, int layo
             ua.row_loss = want_loss ? ws.row_loss : nullptr;
             ua.stats = stats_dev ? stats_dev + l * NAT_RVQ_STAT_FIELDS : nullptr;
             ua.n = n; ua.K = cb->K; ua.dp = cb->dp; ua.code_dtype = code_dtype;
-            const int scan_grid = cb->sm_count * 8;
+            const int scan_grid = cb->sm_count * 4;
+            const size_t scan_smem = static_cast<size_t>(cb->dp) * sizeof(float);
             if (!exact) {
                 NAT_LAUNCH(1, st, gemm::rvq_gemm_top4_kernel<false><<<std::min(n_tiles, cb->sm_count), gemm::NUM_THREADS,
                                                     gemm::SMEM_BYTES, st>>>(
@@ -358,9 +367,11 @@ int nat_rvq_encode_f32(const nat_rvq_codebooks* cb, const float* x_dev, int layo
                     ws.rowinfo, cb->cn32 + static_cast<long long>(l) * cb->kp, ws.cand, nullptr, 0));
                 NAT_LAUNCH(2, st, rows::decide_update_kernel<<<std::min((n + 7) / 8, cb->sm_count * 16), 256, 0, st>>>(
                     ua, ws.cand, ws.scan_list, ws.scan_count + l));
-                NAT_LAUNCH(3, st, rows::full_scan_kernel<<<scan_grid, 256, 0, st>>>(ua, ws.scan_list, ws.scan_count + l, 0, false));
+                NAT_LAUNCH(3, st, rows::full_scan_kernel<<<scan_grid, rows::kScanThreads, scan_smem, st>>>(
+                    ua, ws.scan_list, ws.scan_count + l, 0, false));
             } else {
-                NAT_LAUNCH(3, st, rows::full_scan_kernel<<<std::min(n, scan_grid), 256, 0, st>>>(ua, nullptr, nullptr, n, true));
+                NAT_LAUNCH(3, st, rows::full_scan_kernel<<<std::min(n, scan_grid), rows::kScanThreads, scan_smem, st>>>(
+                    ua, nullptr, nullptr, n, true));
             }
             if (want_loss) NAT_LAUNCH(4, st, rows::reduce_loss_kernel<<<1, 1024, 0, st>>>(ws.row_loss, n, ws.loss_acc + l));
             NAT_CUDA(cudaGetLastError());

@@ -40,6 +40,27 @@ __device__ __forceinline__ float pow2_scale_for(float amax) {
     return __uint_as_float(static_cast<uint32_t>(127 - e) << 23);
 }
 
+// {alpha, bias, window, sx} of one frame from its scale and the three sums over the scaled row:
+//   lo2 = ||x_hat - fp16(x_hat)||^2,  xt2 = ||fp16(x_hat)||^2,  xh2 = ||x_hat||^2        (x_hat = r * sx)
+// Error budget of the coarse score (DESIGN.md "Exactness"): |dot error| <= lo*chat + xt*clo + gamma*xt*ctil.
+__device__ __forceinline__ float4 make_rowinfo(float sx, float lo2, float xt2, float xh2,
+                                               const LayerConst* __restrict__ lc, int d_pad) {
+    const float up = 1.0005f;                                  // covers the fp32 rounding of the sums
+    const float inv = 1.f / (sx * lc->sc);                     // exact: both are powers of two
+    const float rn2 = xh2 * up / (sx * sx);
+    const float xt = sqrtf(xt2 * up), lo = sqrtf(lo2 * up);
+    const float gamma = kGammaPerK * static_cast<float>(d_pad);
+    const float e_dot = lo * lc->chat_max + xt * lc->clo_max + gamma * xt * lc->ctil_max;
+    const float e_abs = 9.5367431640625e-07f * (rn2 + lc->cmax2);   // 2^-20: fp32 epilogue + ||c||^2 rounding
+    const float E = 2.f * inv * e_dot * up + e_abs + 1e-30f;
+    float4 ri;
+    ri.x = -2.f * inv;                                         // alpha: score = acc * alpha + ||c||^2 + bias
+    ri.y = (rn2 + E) * 1.001f;                                 // bias: keeps every shifted score >= 0
+    ri.z = 2.f * E;                                            // decision window
+    ri.w = sx;
+    return ri;
+}
+
 // Second half of every row producer: given the fp32 row already in global memory, emit the fp16 operand row and the
 // {alpha, bias, window} triple the coarse pass and the decision need. Warp-collective.
 __device__ __forceinline__ void finalize_row(const float4* r4, int dp4, float amax_lane,
@@ -70,22 +91,7 @@ __device__ __forceinline__ void finalize_row(const float4* r4, int dp4, float am
     lo2 = warp_sum(lo2);
     xt2 = warp_sum(xt2);
     xh2 = warp_sum(xh2);
-    if (lane == 0) {
-        const float up = 1.0005f;                                  // covers the fp32 rounding of the sums above
-        const float inv = 1.f / (sx * lc->sc);                     // exact: both are powers of two
-        const float rn2 = xh2 * up / (sx * sx);
-        const float xt = sqrtf(xt2 * up), lo = sqrtf(lo2 * up);
-        const float gamma = kGammaPerK * static_cast<float>(d_pad);
-        const float e_dot = lo * lc->chat_max + xt * lc->clo_max + gamma * xt * lc->ctil_max;
-        const float e_abs = 9.5367431640625e-07f * (rn2 + lc->cmax2);   // 2^-20: fp32 epilogue + ||c||^2 rounding
-        const float E = 2.f * inv * e_dot * up + e_abs + 1e-30f;
-        float4 ri;
-        ri.x = -2.f * inv;                                         // alpha: score = acc * alpha + ||c||^2 + bias
-        ri.y = (rn2 + E) * 1.001f;                                 // bias: keeps every shifted score >= 0
-        ri.z = 2.f * E;                                            // decision window
-        ri.w = sx;
-        *rowinfo_out = ri;
-    }
+    if (lane == 0) *rowinfo_out = make_rowinfo(sx, lo2, xt2, xh2, lc, d_pad);
 }
 
 // ---------------------------------------------------------------------------------------------------- layer 0 prep
@@ -116,6 +122,65 @@ prep_rows_kernel(const float* __restrict__ x, long long x_ld, int n, int D, int 
         }
         finalize_row(reinterpret_cast<const float4*>(rr), dp / 4, amax,
                      reinterpret_cast<uint2*>(a + static_cast<long long>(row) * dp), rowinfo + row, lc, dp);
+    }
+}
+
+// Fused layer-0 preparation for the [B, D, T] layout: 32 frames x all features go through shared memory once
+// (coalesced 128-byte reads along time), then each warp turns 4 frames into fp32 rows, fp16 operand rows and the
+// {alpha, bias, window} triple. One HBM read of x, one write of r and A. Dynamic smem: 32 * (dp + 1) floats.
+constexpr int kPrepFrames = 32;
+__global__ void __launch_bounds__(256)
+prep_bct_fused_kernel(const float* __restrict__ x, long long T, int D, long long n0, int n, int dp,
+                      float* __restrict__ r, __half* __restrict__ a, float4* __restrict__ rowinfo,
+                      const LayerConst* __restrict__ lc) {
+    extern __shared__ float s_tile[];                   // [32][dp + 1]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ld = dp + 1;
+    const int f0 = blockIdx.x * kPrepFrames;
+    const int f = f0 + lane;
+    long long src = -1;
+    if (f < n) {
+        const long long g = n0 + f, b = g / T, t = g - b * T;
+        src = b * D * T + t;
+    }
+    // lane = frame (consecutive t: one 128-byte line per feature), warps stride over features, 8 loads in flight
+    for (int d0 = warp * 8; d0 < dp; d0 += 64) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int d = d0 + u;
+            v[u] = (src >= 0 && d < D) ? __ldg(x + src + static_cast<long long>(d) * T) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (d0 + u < dp) s_tile[lane * ld + d0 + u] = v[u];
+    }
+    __syncthreads();
+    for (int fr = warp; fr < kPrepFrames; fr += 8) {
+        const int row = f0 + fr;
+        if (row >= n) break;                            // warp-uniform
+        const float* src_row = s_tile + fr * ld;
+        float amax = 0.f;
+        for (int i = lane; i < dp; i += 32) amax = fmaxf(amax, fabsf(src_row[i]));
+        amax = warp_max(amax);
+        const float sx = pow2_scale_for(amax);
+        float* rr = r + static_cast<long long>(row) * dp;
+        __half* ar = a + static_cast<long long>(row) * dp;
+        float lo2 = 0.f, xt2 = 0.f, xh2 = 0.f;
+        for (int i = lane; i < dp; i += 32) {
+            const float v = src_row[i];
+            const float xs = v * sx;
+            const __half h = __float2half_rn(xs);
+            const float hf = __half2float(h);
+            const float lo = xs - hf;
+            lo2 = fmaf(lo, lo, lo2);
+            xt2 = fmaf(hf, hf, xt2);
+            xh2 = fmaf(xs, xs, xh2);
+            rr[i] = v;
+            ar[i] = h;
+        }
+        lo2 = warp_sum(lo2); xt2 = warp_sum(xt2); xh2 = warp_sum(xh2);
+        if (lane == 0) rowinfo[row] = make_rowinfo(sx, lo2, xt2, xh2, lc, dp);
     }
 }
 
@@ -208,6 +273,10 @@ struct UpdateArgs {
 __device__ __forceinline__ void apply_code(const UpdateArgs& p, int row, int j) {
     const int lane = threadIdx.x & 31;
     const int dp4 = p.dp >> 2;
+    if (p.lc_next == nullptr && p.row_loss == nullptr) {      // last layer, codes only: the residual is dead
+        if (lane == 0) store_code(p.codes, p.code_dtype, row, j);
+        return;
+    }
     float4* r4 = reinterpret_cast<float4*>(p.r + static_cast<long long>(row) * p.dp);
     const float4* c4 = reinterpret_cast<const float4*>(p.cb + static_cast<long long>(j) * p.dp);
     float amax = 0.f;
@@ -294,31 +363,64 @@ decide_update_kernel(UpdateArgs p, const gemm::Cand* __restrict__ cand, int* __r
     }
 }
 
-// Exact full scan, one CTA (8 warps) per listed frame; scan_list == nullptr means "every frame 0..count".
-__global__ void __launch_bounds__(256)
+// Exact full scan: one CTA of 16 warps per listed frame; scan_list == nullptr means "every frame 0..count".
+// The frame sits in shared memory; each warp scores four codes per sweep so 24+ independent 16-byte loads are in
+// flight per lane (the scan is L2-latency bound, not flop bound).
+constexpr int kScanThreads = 512;
+constexpr int kScanWarps = kScanThreads / 32;
+constexpr int kScanCodes = 4;
+
+__global__ void __launch_bounds__(kScanThreads)
 full_scan_kernel(UpdateArgs p, const int* __restrict__ scan_list, const int* __restrict__ scan_count,
                  int count_if_all, bool count_stats) {
-    __shared__ double s_best[8];
-    __shared__ int s_idx[8];
+    extern __shared__ float4 s_row[];                   // [dp / 4]
+    __shared__ double s_best[kScanWarps];
+    __shared__ int s_idx[kScanWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int dp4 = p.dp >> 2;
     const int count = scan_list != nullptr ? *scan_count : count_if_all;
     for (int e = blockIdx.x; e < count; e += gridDim.x) {
         const int row = scan_list != nullptr ? scan_list[e] : e;
         const float4* r4 = reinterpret_cast<const float4*>(p.r + static_cast<long long>(row) * p.dp);
+        for (int i = threadIdx.x; i < dp4; i += kScanThreads) s_row[i] = r4[i];
+        __syncthreads();
         double best = 0.0;
         int bestj = -1;
-        for (int k = warp; k < p.K; k += 8) {
-            const double s = exact_score(r4, reinterpret_cast<const float4*>(p.cb + static_cast<long long>(k) * p.dp),
-                                         dp4, p.cn64[k]);
-            if (bestj < 0 || s < best) { best = s; bestj = k; }   // k ascending within a warp: first minimum kept
+        for (int k0 = warp * kScanCodes; k0 < p.K; k0 += kScanWarps * kScanCodes) {
+            double acc[kScanCodes];
+            const float4* c4[kScanCodes];
+#pragma unroll
+            for (int c = 0; c < kScanCodes; ++c) {
+                acc[c] = 0.0;
+                c4[c] = reinterpret_cast<const float4*>(p.cb + static_cast<long long>(min(k0 + c, p.K - 1)) * p.dp);
+            }
+            for (int i = lane; i < dp4; i += 32) {
+                const float4 a = s_row[i];
+#pragma unroll
+                for (int c = 0; c < kScanCodes; ++c) {
+                    const float4 b = __ldg(c4[c] + i);
+                    acc[c] = fma(static_cast<double>(a.x), static_cast<double>(b.x), acc[c]);
+                    acc[c] = fma(static_cast<double>(a.y), static_cast<double>(b.y), acc[c]);
+                    acc[c] = fma(static_cast<double>(a.z), static_cast<double>(b.z), acc[c]);
+                    acc[c] = fma(static_cast<double>(a.w), static_cast<double>(b.w), acc[c]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < kScanCodes; ++c) {
+                const int k = k0 + c;
+                const double dot = warp_sum(acc[c]);
+                if (k < p.K) {
+                    const double sc = p.cn64[k] - 2.0 * dot;
+                    if (bestj < 0 || sc < best) { best = sc; bestj = k; }   // k ascending: first minimum kept
+                }
+            }
         }
         if (lane == 0) { s_best[warp] = best; s_idx[warp] = bestj; }
         __syncthreads();
         if (warp == 0) {
             double b = 0.0;
             int bj = -1;
-            for (int w = 0; w < 8; ++w) {
+            for (int w = 0; w < kScanWarps; ++w) {
                 const int wj = s_idx[w];
                 if (wj < 0) continue;
                 if (bj < 0 || s_best[w] < b || (s_best[w] == b && wj < bj)) { b = s_best[w]; bj = wj; }
