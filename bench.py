@@ -271,9 +271,10 @@ def main():
     for _ in range(prof_reps):
         for i, h in enumerate(handles):
             out = codes[i * LAYERS_PER_STACK:(i + 1) * LAYERS_PER_STACK]
+            # single-stream so that every launch is timed alone and covers all n_local frames
             _lib.check(lib.nat_rvq_encode_profile_f32(h, x.data_ptr(), _lib.LAYOUT_BCT, 1, n_local, out.data_ptr(),
                                                       _lib.CODES_I16, None, None, 0.25, None, ws.data_ptr(), ws_bytes,
-                                                      0, stream.cuda_stream, prof))
+                                                      _lib.RVQ_SINGLE_STREAM, stream.cuda_stream, prof))
             for k in range(_lib.PROF_FIELDS):
                 prof_sum[k] += prof[k]
     gemm_launches = prof_sum[6]

@@ -48,8 +48,11 @@ enum nat_code_dtype {
 
 enum nat_rvq_flags {
     NAT_RVQ_DEFAULT = 0,
-    NAT_RVQ_EXACT_SCAN = 1          /* skip the tensor-core pass: every frame takes the exact fp64 full scan (slow;
+    NAT_RVQ_EXACT_SCAN = 1,         /* skip the tensor-core pass: every frame takes the exact fp64 full scan (slow;
                                        used by tests as an on-device cross-check and for tiny latency-bound calls)   */
+    NAT_RVQ_SINGLE_STREAM = 2       /* keep every kernel on `stream`: by default long inputs are split over two
+                                       internal streams (forked from / joined to `stream`) so the HBM-bound row
+                                       kernels of one half overlap the tensor-bound GEMM of the other              */
 };
 
 const char* nat_last_error(void);

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_PKG_DIR, "libnat_b200.so")
 NAT_OK = 0
 LAYOUT_BCT, LAYOUT_ROWS = 0, 1
 CODES_I64, CODES_I32, CODES_I16 = 0, 1, 2
-RVQ_DEFAULT, RVQ_EXACT_SCAN = 0, 1
+RVQ_DEFAULT, RVQ_EXACT_SCAN, RVQ_SINGLE_STREAM = 0, 1, 2
 STAT_FIELDS = 4
 PROF_FIELDS = 8
 PROF_NAMES = ("prep", "gemm", "decide_update", "full_scan", "loss", "output", "gemm_launches", "wall")

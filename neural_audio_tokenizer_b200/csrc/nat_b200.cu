@@ -168,6 +168,9 @@ struct nat_rvq_codebooks {
     size_t host_arena_bytes;
     cudaStream_t copy_stream;
     cudaEvent_t ev[4];
+    // internal streams of the two-lane encode (created on first use)
+    cudaStream_t side[2];
+    cudaEvent_t side_ev[3];
 };
 
 extern "C" {
@@ -267,6 +270,8 @@ int nat_rvq_codebooks_destroy(nat_rvq_codebooks* cb) {
     cudaFree(cb->scratch); cudaFree(cb->host_arena_dev);
     if (cb->copy_stream) cudaStreamDestroy(cb->copy_stream);
     for (auto& e : cb->ev) if (e) cudaEventDestroy(e);
+    for (auto& s2 : cb->side) if (s2) cudaStreamDestroy(s2);
+    for (auto& e : cb->side_ev) if (e) cudaEventDestroy(e);
     delete cb;
     return NAT_OK;
 }
@@ -309,11 +314,85 @@ static int launch_layer0_prep(const nat_rvq_codebooks* cb, const Workspace& ws, 
     return NAT_OK;
 }
 
-int nat_rvq_encode_f32(const nat_rvq_codebooks* cb, const float* x_dev, int layout, int64_t B, int64_t T,
+// Everything one chunk of frames [n0, n0 + n) needs, in order, on one stream.
+struct EncodeCall {
+    const nat_rvq_codebooks* cb;
+    const float* x; int layout; long long T, N;
+    void* codes; int code_dtype; float* quantized; bool want_loss; unsigned long long* stats; bool exact;
+};
+
+static int encode_chunk(const EncodeCall& c, const Workspace& ws, const CUtensorMap& map_a, long long n0, int n,
+                        cudaStream_t st) {
+    using namespace nat;
+    const nat_rvq_codebooks* cb = c.cb;
+    const int cbytes = code_bytes(c.code_dtype);
+    const long long cb_layer_ld = static_cast<long long>(cb->K) * cb->dp;
+    if (int rc = launch_layer0_prep(cb, ws, c.x, c.layout, c.T, n0, n, st)) return rc;
+    NAT_CUDA(cudaMemsetAsync(ws.scan_count, 0, sizeof(int) * cb->L, st));
+    const int n_tiles = (n + gemm::BLOCK_M - 1) / gemm::BLOCK_M;
+    for (int l = 0; l < cb->L; ++l) {
+        rows::UpdateArgs ua;
+        ua.r = ws.r; ua.a = ws.a; ua.rowinfo = ws.rowinfo;
+        ua.cb = cb->cbf + l * cb_layer_ld;
+        ua.cn64 = cb->cn64 + static_cast<long long>(l) * cb->K;
+        ua.lc_next = (l + 1 < cb->L) ? cb->lc + l + 1 : nullptr;
+        ua.codes = static_cast<char*>(c.codes) + (static_cast<long long>(l) * c.N + n0) * cbytes;
+        ua.row_loss = c.want_loss ? ws.row_loss : nullptr;
+        ua.stats = c.stats ? c.stats + l * NAT_RVQ_STAT_FIELDS : nullptr;
+        ua.n = n; ua.K = cb->K; ua.dp = cb->dp; ua.code_dtype = c.code_dtype;
+        const int scan_grid = cb->sm_count * 4;
+        const size_t scan_smem = static_cast<size_t>(cb->dp) * sizeof(float);
+        if (!c.exact) {
+            NAT_LAUNCH(1, st, gemm::rvq_gemm_top4_kernel<false><<<std::min(n_tiles, cb->sm_count), gemm::NUM_THREADS,
+                                                                   gemm::SMEM_BYTES, st>>>(
+                map_a, cb->map_b, n, n_tiles, cb->kp / gemm::BLOCK_N, cb->dp / gemm::BLOCK_K, l * cb->kp, ws.rowinfo,
+                cb->cn32 + static_cast<long long>(l) * cb->kp, ws.cand, nullptr, 0));
+            NAT_LAUNCH(2, st, rows::decide_update_kernel<<<std::min((n + 7) / 8, cb->sm_count * 16), 256, 0, st>>>(
+                ua, ws.cand, ws.scan_list, ws.scan_count + l));
+            NAT_LAUNCH(3, st, rows::full_scan_kernel<<<scan_grid, rows::kScanThreads, scan_smem, st>>>(
+                ua, ws.scan_list, ws.scan_count + l, 0, false));
+        } else {
+            NAT_LAUNCH(3, st, rows::full_scan_kernel<<<std::min(n, scan_grid), rows::kScanThreads, scan_smem, st>>>(
+                ua, nullptr, nullptr, n, true));
+        }
+        if (c.want_loss) NAT_LAUNCH(4, st, rows::reduce_loss_kernel<<<1, 1024, 0, st>>>(ws.row_loss, n, ws.loss_acc + l));
+        NAT_CUDA(cudaGetLastError());
+    }
+    if (c.quantized != nullptr) {
+        // replay the chain from the emitted codes on a fresh copy of x (bit-identical op order, nat.py:2167/1405/1408)
+        const int warps_grid = std::min((n + 7) / 8, cb->sm_count * 16);
+        if (c.layout == NAT_LAYOUT_ROWS) {
+            NAT_LAUNCH(0, st, rows::prep_rows_kernel<<<warps_grid, 256, 0, st>>>(c.x + n0 * cb->D, cb->D, n, cb->D, cb->dp,
+                                                                              ws.r, ws.a, ws.rowinfo, cb->lc, false));
+        } else {
+            dim3 grid((n + 31) / 32, cb->dp / 32);
+            NAT_LAUNCH(0, st, rows::bct_to_rows_kernel<<<grid, 256, 0, st>>>(c.x, c.T, cb->D, n0, n, cb->dp, ws.r));
+        }
+        NAT_LAUNCH(5, st, rows::reconstruct_rows_kernel<<<warps_grid, 256, 0, st>>>(ws.r, n, cb->dp, cb->cbf, cb_layer_ld,
+                                                                                 cb->L, c.codes, c.code_dtype, c.N, n0));
+        if (c.layout == NAT_LAYOUT_ROWS) {
+            NAT_LAUNCH(5, st, rows::copy_rows_out_kernel<<<cb->sm_count * 8, 256, 0, st>>>(ws.r, n, cb->dp, cb->D,
+                                                                                        c.quantized + n0 * cb->D));
+        } else {
+            dim3 grid((n + 31) / 32, (cb->D + 31) / 32);
+            NAT_LAUNCH(5, st, rows::rows_to_bct_kernel<<<grid, 256, 0, st>>>(ws.r, cb->dp, c.T, cb->D, n0, n, c.quantized));
+        }
+        NAT_CUDA(cudaGetLastError());
+    }
+    return NAT_OK;
+}
+
+static bool overlap_enabled() {
+    static bool on = [] { const char* e = getenv("NAT_RVQ_STREAMS"); return !(e && atoi(e) == 1); }();
+    return on;
+}
+
+int nat_rvq_encode_f32(const nat_rvq_codebooks* cb_const, const float* x_dev, int layout, int64_t B, int64_t T,
                        void* codes_out_dev, int code_dtype, float* quantized_out_dev, float* loss_out_dev,
                        float commitment_weight, unsigned long long* stats_dev, void* workspace_dev,
                        size_t workspace_bytes, int flags, void* stream) {
     using namespace nat;
+    nat_rvq_codebooks* cb = const_cast<nat_rvq_codebooks*>(cb_const);
     if (cb == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null codebook handle");
     if (B < 0 || T < 0) return fail(NAT_ERR_INVALID_ARGUMENT, "negative batch or time extent");
     if (layout != NAT_LAYOUT_BCT && layout != NAT_LAYOUT_ROWS) return fail(NAT_ERR_INVALID_ARGUMENT, "bad layout %d", layout);
@@ -329,78 +408,55 @@ int nat_rvq_encode_f32(const nat_rvq_codebooks* cb, const float* x_dev, int layo
     if (dev != cb->device) return fail(NAT_ERR_INVALID_ARGUMENT, "codebooks live on device %d, current device is %d", cb->device, dev);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
-    Workspace ws;
-    if (!carve(workspace_dev, workspace_bytes, cb->dp, std::min<long long>(N, chunk_cap_rows()), &ws))
-        return fail(NAT_ERR_WORKSPACE, "workspace of %zu bytes cannot hold one 128-frame tile (need %zu)", workspace_bytes,
-                    nat_rvq_workspace_bytes(cb, 128));
-    CUtensorMap map_a;
-    if (int rc = make_map_f16(&map_a, ws.a, ws.rows, cb->dp, 128)) return rc;
-
-    const bool exact = (flags & NAT_RVQ_EXACT_SCAN) != 0;
-    const bool want_loss = loss_out_dev != nullptr;
-    const int cbytes = code_bytes(code_dtype);
-    const long long cb_layer_ld = static_cast<long long>(cb->K) * cb->dp;
-    NAT_CUDA(cudaMemsetAsync(ws.loss_acc, 0, sizeof(double) * cb->L, st));
-    if (cb->dp != cb->D) NAT_CUDA(cudaMemsetAsync(ws.a, 0, static_cast<size_t>(ws.rows) * cb->dp * 2, st));
-
-    for (long long n0 = 0; n0 < N; n0 += ws.rows) {
-        const int n = static_cast<int>(std::min<long long>(ws.rows, N - n0));
-        if (int rc = launch_layer0_prep(cb, ws, x_dev, layout, T, n0, n, st)) return rc;
-        NAT_CUDA(cudaMemsetAsync(ws.scan_count, 0, sizeof(int) * cb->L, st));
-        const int n_tiles = (n + gemm::BLOCK_M - 1) / gemm::BLOCK_M;
-        for (int l = 0; l < cb->L; ++l) {
-            rows::UpdateArgs ua;
-            ua.r = ws.r; ua.a = ws.a; ua.rowinfo = ws.rowinfo;
-            ua.cb = cb->cbf + l * cb_layer_ld;
-            ua.cn64 = cb->cn64 + static_cast<long long>(l) * cb->K;
-            ua.lc_next = (l + 1 < cb->L) ? cb->lc + l + 1 : nullptr;
-            ua.codes = static_cast<char*>(codes_out_dev) + (static_cast<long long>(l) * N + n0) * cbytes;
-            ua.row_loss = want_loss ? ws.row_loss : nullptr;
-            ua.stats = stats_dev ? stats_dev + l * NAT_RVQ_STAT_FIELDS : nullptr;
-            ua.n = n; ua.K = cb->K; ua.dp = cb->dp; ua.code_dtype = code_dtype;
-            const int scan_grid = cb->sm_count * 4;
-            const size_t scan_smem = static_cast<size_t>(cb->dp) * sizeof(float);
-            if (!exact) {
-                NAT_LAUNCH(1, st, gemm::rvq_gemm_top4_kernel<false><<<std::min(n_tiles, cb->sm_count), gemm::NUM_THREADS,
-                                                    gemm::SMEM_BYTES, st>>>(
-                    map_a, cb->map_b, n, n_tiles, cb->kp / gemm::BLOCK_N, cb->dp / gemm::BLOCK_K, l * cb->kp,
-                    ws.rowinfo, cb->cn32 + static_cast<long long>(l) * cb->kp, ws.cand, nullptr, 0));
-                NAT_LAUNCH(2, st, rows::decide_update_kernel<<<std::min((n + 7) / 8, cb->sm_count * 16), 256, 0, st>>>(
-                    ua, ws.cand, ws.scan_list, ws.scan_count + l));
-                NAT_LAUNCH(3, st, rows::full_scan_kernel<<<scan_grid, rows::kScanThreads, scan_smem, st>>>(
-                    ua, ws.scan_list, ws.scan_count + l, 0, false));
-            } else {
-                NAT_LAUNCH(3, st, rows::full_scan_kernel<<<std::min(n, scan_grid), rows::kScanThreads, scan_smem, st>>>(
-                    ua, nullptr, nullptr, n, true));
-            }
-            if (want_loss) NAT_LAUNCH(4, st, rows::reduce_loss_kernel<<<1, 1024, 0, st>>>(ws.row_loss, n, ws.loss_acc + l));
-            NAT_CUDA(cudaGetLastError());
+    // Two halves of the workspace on two internal streams: the HBM-bound row kernels of one half run under the
+    // tensor-bound GEMM of the other. Small inputs (or NAT_RVQ_SINGLE_STREAM / NAT_RVQ_STREAMS=1) stay on `st`.
+    const bool two = overlap_enabled() && !(flags & NAT_RVQ_SINGLE_STREAM) && N >= 4LL * 128 * cb->sm_count;
+    const int n_lanes = two ? 2 : 1;
+    Workspace ws[2];
+    CUtensorMap map_a[2];
+    const size_t half_bytes = (workspace_bytes / n_lanes) & ~static_cast<size_t>(255);
+    const long long want = std::min<long long>((N + n_lanes - 1) / n_lanes, chunk_cap_rows());
+    for (int i = 0; i < n_lanes; ++i) {
+        if (!carve(static_cast<char*>(workspace_dev) + i * half_bytes, half_bytes, cb->dp, want, &ws[i]))
+            return fail(NAT_ERR_WORKSPACE, "workspace of %zu bytes cannot hold one 128-frame tile per lane (need %zu)",
+                        workspace_bytes, nat_rvq_workspace_bytes(cb, 128 * n_lanes));
+        if (int rc = make_map_f16(&map_a[i], ws[i].a, ws[i].rows, cb->dp, 128)) return rc;
+    }
+    cudaStream_t lane_st[2] = {st, st};
+    if (two) {
+        if (cb->side[0] == nullptr) {
+            for (int i = 0; i < 2; ++i) NAT_CUDA(cudaStreamCreateWithFlags(&cb->side[i], cudaStreamNonBlocking));
+            for (auto& e : cb->side_ev) NAT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         }
-        if (quantized_out_dev != nullptr) {
-            // replay the chain from the emitted codes on a fresh copy of x (bit-identical op order, nat.py:2167/1405/1408)
-            const int warps_grid = std::min((n + 7) / 8, cb->sm_count * 16);
-            if (layout == NAT_LAYOUT_ROWS) {
-                NAT_LAUNCH(0, st, rows::prep_rows_kernel<<<warps_grid, 256, 0, st>>>(x_dev + n0 * cb->D, cb->D, n, cb->D, cb->dp, ws.r,
-                                                                   ws.a, ws.rowinfo, cb->lc, false));
-            } else {
-                dim3 grid((n + 31) / 32, cb->dp / 32);
-                NAT_LAUNCH(0, st, rows::bct_to_rows_kernel<<<grid, 256, 0, st>>>(x_dev, T, cb->D, n0, n, cb->dp, ws.r));
-            }
-            NAT_LAUNCH(5, st, rows::reconstruct_rows_kernel<<<warps_grid, 256, 0, st>>>(ws.r, n, cb->dp, cb->cbf, cb_layer_ld, cb->L,
-                                                                      codes_out_dev, code_dtype, N, n0));
-            if (layout == NAT_LAYOUT_ROWS) {
-                NAT_LAUNCH(5, st, rows::copy_rows_out_kernel<<<cb->sm_count * 8, 256, 0, st>>>(ws.r, n, cb->dp, cb->D,
-                                                                            quantized_out_dev + n0 * cb->D));
-            } else {
-                dim3 grid((n + 31) / 32, (cb->D + 31) / 32);
-                NAT_LAUNCH(5, st, rows::rows_to_bct_kernel<<<grid, 256, 0, st>>>(ws.r, cb->dp, T, cb->D, n0, n, quantized_out_dev));
-            }
-            NAT_CUDA(cudaGetLastError());
+        NAT_CUDA(cudaEventRecord(cb->side_ev[0], st));
+        for (int i = 0; i < 2; ++i) {
+            NAT_CUDA(cudaStreamWaitEvent(cb->side[i], cb->side_ev[0], 0));
+            lane_st[i] = cb->side[i];
         }
     }
-    if (want_loss) {
-        NAT_LAUNCH(4, st, rows::finish_loss_kernel<<<1, 32, 0, st>>>(ws.loss_acc, cb->L, static_cast<double>(N) * cb->D,
-                                                   commitment_weight, loss_out_dev));
+
+    EncodeCall call{cb, x_dev, layout, T, N, codes_out_dev, code_dtype, quantized_out_dev, loss_out_dev != nullptr,
+                    stats_dev, (flags & NAT_RVQ_EXACT_SCAN) != 0};
+    for (int i = 0; i < n_lanes; ++i) {
+        NAT_CUDA(cudaMemsetAsync(ws[i].loss_acc, 0, sizeof(double) * cb->L, lane_st[i]));
+        if (cb->dp != cb->D) NAT_CUDA(cudaMemsetAsync(ws[i].a, 0, static_cast<size_t>(ws[i].rows) * cb->dp * 2, lane_st[i]));
+    }
+    int lane = 0;
+    for (long long n0 = 0; n0 < N; lane = (lane + 1) % n_lanes) {
+        const int n = static_cast<int>(std::min<long long>(ws[lane].rows, N - n0));
+        if (int rc = encode_chunk(call, ws[lane], map_a[lane], n0, n, lane_st[lane])) return rc;
+        n0 += n;
+    }
+    if (two) {
+        for (int i = 0; i < 2; ++i) {
+            NAT_CUDA(cudaEventRecord(cb->side_ev[1 + i], cb->side[i]));
+            NAT_CUDA(cudaStreamWaitEvent(st, cb->side_ev[1 + i], 0));
+        }
+    }
+    if (loss_out_dev != nullptr) {
+        NAT_LAUNCH(4, st, rows::finish_loss_kernel<<<1, 32, 0, st>>>(ws[0].loss_acc, two ? ws[1].loss_acc : nullptr, cb->L,
+                                                                   static_cast<double>(N) * cb->D, commitment_weight,
+                                                                   loss_out_dev));
         NAT_CUDA(cudaGetLastError());
     }
     return NAT_OK;

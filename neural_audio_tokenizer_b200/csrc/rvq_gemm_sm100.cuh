@@ -44,8 +44,10 @@ __device__ __forceinline__ void top4_insert(int v, int& m0, int& m1, int& m2, in
 }
 
 // DUMP=true writes the raw accumulators instead of candidates (validation of the MMA path, tests only).
+// minBlocks = 2 only caps registers at 168 per thread (shared memory still admits one CTA per SM): the freed
+// register file lets the HBM-bound row kernels of the other stream co-reside with this kernel.
 template <bool DUMP>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_THREADS, 2)
 rvq_gemm_top4_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, Dp], box 64 x 128, SWIZZLE_128B
                      const __grid_constant__ CUtensorMap map_b,   // fp16 [L*Kp, Dp], box 64 x 256, SWIZZLE_128B
                      int n_rows, int n_tiles, int n_chunks, int n_kblocks, int b_row0,

@@ -447,11 +447,12 @@ reduce_loss_kernel(const double* __restrict__ row_loss, int n, double* __restric
     }
     if (threadIdx.x == 0) *acc += sh[0];
 }
-__global__ void finish_loss_kernel(const double* __restrict__ acc, int L, double count, float w,
-                                   float* __restrict__ loss_out) {
+__global__ void finish_loss_kernel(const double* __restrict__ acc, const double* __restrict__ acc2, int L, double count,
+                                   float w, float* __restrict__ loss_out) {
     const int l = threadIdx.x;
     if (l < L) {
-        const float mse = static_cast<float>(acc[l] / count);
+        const double total = acc2 != nullptr ? acc[l] + acc2[l] : acc[l];     // the two lanes, fixed order
+        const float mse = static_cast<float>(total / count);
         loss_out[l] = __fadd_rn(mse, __fmul_rn(w, mse));           // q_latent + w * e_latent, nat.py:2164
     }
 }

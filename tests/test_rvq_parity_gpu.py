@@ -255,3 +255,39 @@ def test_pipeline_fixture_tokens():
         assert all(not c.is_cuda for c in codes)
         got = np.stack([c[0].numpy() for c in codes], axis=1)
         np.testing.assert_array_equal(got, g[key])
+
+
+def test_two_lane_overlap_matches_single_stream():
+    """Long inputs are split over two internal streams; indices and the quantised sum must not depend on that."""
+    from neural_audio_tokenizer_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(8)
+    L, K, D, N = 4, 512, 256, 90_000
+    cbs = [torch.randn(K, D, device="cuda") for _ in range(L)]
+    x = torch.randn(1, D, N, device="cuda")
+    ptrs = (ctypes.c_void_p * L)(*[c.data_ptr() for c in cbs])
+    handle = ctypes.c_void_p()
+    _lib.check(lib.nat_rvq_codebooks_create(ptrs, L, K, D, None, ctypes.byref(handle)))
+    try:
+        ws_bytes = lib.nat_rvq_workspace_bytes(handle, N)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+        outs = []
+        for flags in (0, _lib.RVQ_SINGLE_STREAM):
+            codes = torch.empty((L, N), dtype=torch.int32, device="cuda")
+            q = torch.empty_like(x)
+            loss = torch.empty(L, device="cuda")
+            stats = torch.zeros((L, 4), dtype=torch.int64, device="cuda")
+            _lib.check(lib.nat_rvq_encode_f32(handle, x.data_ptr(), _lib.LAYOUT_BCT, 1, N, codes.data_ptr(),
+                                              _lib.CODES_I32, q.data_ptr(), loss.data_ptr(), 0.25, stats.data_ptr(),
+                                              ws.data_ptr(), ws_bytes, flags,
+                                              torch.cuda.current_stream().cuda_stream))
+            torch.cuda.synchronize()
+            outs.append((codes, q, loss, stats))
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+        assert torch.allclose(outs[0][2], outs[1][2], rtol=1e-6)
+        assert torch.equal(outs[0][3], outs[1][3]) and (outs[0][3][:, :3].sum(dim=1) == N).all()
+        ref = rvq_oracle.rvq_encode(x[:, :, :4000].cpu(), [c.cpu() for c in cbs])
+        _check_codes(x[:, :, :4000].cpu(), torch.stack([c.cpu() for c in cbs]), np.stack([r.numpy() for r in ref]),
+                     outs[0][0][:, :4000].reshape(L, 1, 4000).cpu().numpy())
+    finally:
+        lib.nat_rvq_codebooks_destroy(handle)
