@@ -250,6 +250,16 @@ int nat_rvq_codebooks_create(const float* const* codebooks_dev, int L, int K, in
                                    nat::gemm::SMEM_BYTES), "cudaFuncSetAttribute");
         guard(cudaFuncSetAttribute(nat::rows::prep_bct_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    200 * 1024), "cudaFuncSetAttribute");
+        // An SM cannot host kernels with different shared-memory carve-outs at the same time: ask for the GEMM's
+        // (maximum shared) carve-out on the row kernels too, so they can co-reside with it.
+        guard(cudaFuncSetAttribute(nat::rows::decide_update_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   cudaSharedmemCarveoutMaxShared), "cudaFuncSetAttribute");
+        guard(cudaFuncSetAttribute(nat::rows::full_scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   cudaSharedmemCarveoutMaxShared), "cudaFuncSetAttribute");
+        guard(cudaFuncSetAttribute(nat::rows::prep_bct_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   cudaSharedmemCarveoutMaxShared), "cudaFuncSetAttribute");
+        guard(cudaFuncSetAttribute(nat::rows::prep_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   cudaSharedmemCarveoutMaxShared), "cudaFuncSetAttribute");
     }
     if (rc != NAT_OK) {
         nat_rvq_codebooks_destroy(cb);
@@ -286,8 +296,10 @@ int nat_rvq_codebooks_dims(const nat_rvq_codebooks* cb, int* L, int* K, int* D) 
 
 size_t nat_rvq_workspace_bytes(const nat_rvq_codebooks* cb, int64_t n_frames) {
     if (cb == nullptr || n_frames <= 0) return kWsFixed + 256 * 8 + 128 * ws_per_row(64);
-    const long long rows = std::min<long long>(round_up(n_frames, 128), chunk_cap_rows());
-    return kWsFixed + 256 * 8 + static_cast<size_t>(rows) * ws_per_row(cb->dp);
+    // two lanes, each holding half of the frames rounded up to a tile (see nat_rvq_encode_f32)
+    const long long per_lane = std::min<long long>(round_up((n_frames + 1) / 2, 128), chunk_cap_rows() / 2);
+    const size_t lane_bytes = static_cast<size_t>(round_up(kWsFixed + 256 * 8 + per_lane * ws_per_row(cb->dp), 256));
+    return 2 * lane_bytes;
 }
 
 // ------------------------------------------------------------------------------------------------- encode
