@@ -314,7 +314,7 @@ def main():
         "clocks": clocks.summary(),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
-                     "kernel": "rvq_gemm_top4_kernel", "peak_kind": f"{peaks['source']} sustained bf16 (kernel timed "
+                     "kernel": "rvq_gemm_topk_kernel", "peak_kind": f"{peaks['source']} sustained bf16 (kernel timed "
                      "inside the step)", "frac_of_burst": achieved / peaks["bf16_tflops"],
                      "ms_per_launch": gemm_ms_per_launch, "flop_per_launch": flops_per_launch,
                      "kernel_ms_per_step": kernel_ms},

@@ -130,7 +130,7 @@ struct Workspace {
 
 constexpr size_t kWsFixed = 4096;
 
-size_t ws_per_row(int dp) { return static_cast<size_t>(dp) * 6 + 16 + 32 + 8 + 4; }
+size_t ws_per_row(int dp) { return static_cast<size_t>(dp) * 6 + 16 + sizeof(nat::gemm::Cand) + 8 + 4; }
 
 bool carve(void* base, size_t bytes, int dp, long long want_rows, Workspace* ws) {
     if (bytes <= kWsFixed + 256 * 8) return false;
@@ -145,7 +145,7 @@ bool carve(void* base, size_t bytes, int dp, long long want_rows, Workspace* ws)
     ws->r = reinterpret_cast<float*>(take(static_cast<size_t>(rows) * dp * 4));
     ws->a = reinterpret_cast<__half*>(take(static_cast<size_t>(rows) * dp * 2));
     ws->rowinfo = reinterpret_cast<float4*>(take(static_cast<size_t>(rows) * 16));
-    ws->cand = reinterpret_cast<nat::gemm::Cand*>(take(static_cast<size_t>(rows) * 32));
+    ws->cand = reinterpret_cast<nat::gemm::Cand*>(take(static_cast<size_t>(rows) * sizeof(nat::gemm::Cand)));
     ws->row_loss = reinterpret_cast<double*>(take(static_cast<size_t>(rows) * 8));
     ws->scan_list = reinterpret_cast<int*>(take(static_cast<size_t>(rows) * 4));
     ws->rows = rows;
@@ -244,22 +244,12 @@ int nat_rvq_codebooks_create(const float* const* codebooks_dev, int L, int K, in
     if (rc == NAT_OK) rc = upload_codebooks(cb, codebooks_dev, st);
     if (rc == NAT_OK) rc = make_map_f16(&cb->map_b, cb->cbh, static_cast<long long>(L) * cb->kp, cb->dp, 256);
     if (rc == NAT_OK) {
-        guard(cudaFuncSetAttribute(nat::gemm::rvq_gemm_top4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        guard(cudaFuncSetAttribute(nat::gemm::rvq_gemm_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    nat::gemm::SMEM_BYTES), "cudaFuncSetAttribute");
-        guard(cudaFuncSetAttribute(nat::gemm::rvq_gemm_top4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        guard(cudaFuncSetAttribute(nat::gemm::rvq_gemm_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    nat::gemm::SMEM_BYTES), "cudaFuncSetAttribute");
         guard(cudaFuncSetAttribute(nat::rows::prep_bct_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    200 * 1024), "cudaFuncSetAttribute");
-        // An SM cannot host kernels with different shared-memory carve-outs at the same time: ask for the GEMM's
-        // (maximum shared) carve-out on the row kernels too, so they can co-reside with it.
-        guard(cudaFuncSetAttribute(nat::rows::decide_update_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                   cudaSharedmemCarveoutMaxShared), "cudaFuncSetAttribute");
-        guard(cudaFuncSetAttribute(nat::rows::full_scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                   cudaSharedmemCarveoutMaxShared), "cudaFuncSetAttribute");
-        guard(cudaFuncSetAttribute(nat::rows::prep_bct_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                   cudaSharedmemCarveoutMaxShared), "cudaFuncSetAttribute");
-        guard(cudaFuncSetAttribute(nat::rows::prep_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                   cudaSharedmemCarveoutMaxShared), "cudaFuncSetAttribute");
     }
     if (rc != NAT_OK) {
         nat_rvq_codebooks_destroy(cb);
@@ -355,7 +345,7 @@ static int encode_chunk(const EncodeCall& c, const Workspace& ws, const CUtensor
         const int scan_grid = cb->sm_count * 4;
         const size_t scan_smem = static_cast<size_t>(cb->dp) * sizeof(float);
         if (!c.exact) {
-            NAT_LAUNCH(1, st, gemm::rvq_gemm_top4_kernel<false><<<std::min(n_tiles, cb->sm_count), gemm::NUM_THREADS,
+            NAT_LAUNCH(1, st, gemm::rvq_gemm_topk_kernel<false><<<std::min(n_tiles, cb->sm_count), gemm::NUM_THREADS,
                                                                    gemm::SMEM_BYTES, st>>>(
                 map_a, cb->map_b, n, n_tiles, cb->kp / gemm::BLOCK_N, cb->dp / gemm::BLOCK_K, l * cb->kp, ws.rowinfo,
                 cb->cn32 + static_cast<long long>(l) * cb->kp, ws.cand, nullptr, 0));
@@ -395,7 +385,7 @@ static int encode_chunk(const EncodeCall& c, const Workspace& ws, const CUtensor
 }
 
 static bool overlap_enabled() {
-    static bool on = [] { const char* e = getenv("NAT_RVQ_STREAMS"); return !(e && atoi(e) == 1); }();
+    static bool on = [] { const char* e = getenv("NAT_RVQ_STREAMS"); return e && atoi(e) == 2; }();
     return on;
 }
 
@@ -537,7 +527,7 @@ int nat_debug_rvq_scores(const nat_rvq_codebooks* cb, int layer, const float* ro
     NAT_LAUNCH(0, st, rows::prep_rows_kernel<<<std::min((n + 7) / 8, cb->sm_count * 16), 256, 0, st>>>(
         rows_dev, cb->D, n, cb->D, cb->dp, ws.r, ws.a, ws.rowinfo, cb->lc + layer, false));
     const int n_tiles = (n + gemm::BLOCK_M - 1) / gemm::BLOCK_M;
-    NAT_LAUNCH(1, st, gemm::rvq_gemm_top4_kernel<true><<<std::min(n_tiles, cb->sm_count), gemm::NUM_THREADS, gemm::SMEM_BYTES, st>>>(
+    NAT_LAUNCH(1, st, gemm::rvq_gemm_topk_kernel<true><<<std::min(n_tiles, cb->sm_count), gemm::NUM_THREADS, gemm::SMEM_BYTES, st>>>(
         map_a, cb->map_b, n, n_tiles, cb->kp / gemm::BLOCK_N, cb->dp / gemm::BLOCK_K, layer * cb->kp, ws.rowinfo,
         cb->cn32 + static_cast<long long>(layer) * cb->kp, ws.cand, scores_out_dev, cb->kp));
     NAT_CUDA(cudaGetLastError());

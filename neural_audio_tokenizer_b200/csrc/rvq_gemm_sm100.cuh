@@ -1,15 +1,15 @@
 // Codebook nearest-neighbour search, coarse pass: one layer of  score[n,k] = ||c_k||^2 - 2 r_n.c_k  as an sm_100a
-// tcgen05 GEMM (fp16 operands, fp32 accumulators in TMEM) with the row top-4 kept in the epilogue.
+// tcgen05 GEMM (fp16 operands, fp32 accumulators in TMEM) with the row top-6 kept in the epilogue.
 //
 // Replaces the `torch.cdist` + `argmin` pair of VectorQuantizer.forward (nat.py:2146, 2157).  The [N,K] distance
 // matrix is never materialised: each epilogue thread owns one frame (one TMEM lane) and folds its 256 fresh
-// accumulators per chunk into four packed (score|index) keys.  The exact decision is taken afterwards by
+// accumulators per chunk into six packed (score|index) keys.  The exact decision is taken afterwards by
 // rvq_rows.cuh from these candidates under a proven error bound (DESIGN.md "Exactness").
 //
 // Shape of the kernel (one CTA per SM, persistent over 128-frame tiles):
 //   warp 0      TMA producer: A tile [128 frames x 64] and B tile [256 codes x 64] per K-block, 4-stage ring
 //   warp 1      TMEM owner + single-thread tcgen05.mma issuer, two 256-column accumulator stages
-//   warps 2..5  epilogue: tcgen05.ld 32 columns at a time, score, key, branch-free top-4 insertion
+//   warps 2..5  epilogue: tcgen05.ld 32 columns at a time, score, key, branch-free top-6 insertion
 #pragma once
 
 #include "nat_common.cuh"
@@ -29,18 +29,29 @@ constexpr int TMEM_COLS = 2 * BLOCK_N;
 constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 /*barriers*/ + 1024 /*alignment slack*/;
 constexpr int KEY_INVALID = 0x7FFFFFFF;
 
-// Candidates of one frame after the coarse pass: keys ascending; key = (score bits & ~0xFF) | column-in-chunk,
-// idx = global code index. 32 bytes so that one frame is two 16-byte stores.
-struct __align__(16) Cand {
-    int key[4];
-    uint32_t idx01, idx23, pad0, pad1;
-};
+// Candidates kept per frame. With the fp16 window about 1/6 of the score spacing at the minimum (randn data), the
+// chance that the last kept candidate is still inside the window falls ~6x per extra candidate: 4 -> 1e-3 of the
+// frames need the exact full scan, 6 -> 1e-6. Each candidate costs two integer min/max per score in the epilogue.
+constexpr int NCAND = 6;
 
-__device__ __forceinline__ void top4_insert(int v, int& m0, int& m1, int& m2, int& m3) {
-    int a = min(m0, v); v = max(m0, v); m0 = a;
-    a = min(m1, v);     v = max(m1, v); m1 = a;
-    a = min(m2, v);     v = max(m2, v); m2 = a;
-    m3 = min(m3, v);
+// Candidates of one frame after the coarse pass: keys ascending; key = (score bits & ~0xFF) | column-in-chunk,
+// idx = global code index (16 bit). 48 bytes = three 16-byte stores.
+struct __align__(16) Cand {
+    int key[NCAND];
+    unsigned short idx[NCAND];
+    uint32_t pad[3];
+};
+static_assert(sizeof(Cand) == 48, "Cand layout");
+
+// Branch-free insertion of v into the ascending list m[0..NCAND): 2*NCAND-1 integer min/max.
+__device__ __forceinline__ void topk_insert(int v, int (&m)[NCAND]) {
+#pragma unroll
+    for (int i = 0; i < NCAND - 1; ++i) {
+        const int a = min(m[i], v);
+        v = max(m[i], v);
+        m[i] = a;
+    }
+    m[NCAND - 1] = min(m[NCAND - 1], v);
 }
 
 // DUMP=true writes the raw accumulators instead of candidates (validation of the MMA path, tests only).
@@ -48,7 +59,7 @@ __device__ __forceinline__ void top4_insert(int v, int& m0, int& m1, int& m2, in
 // register file lets the HBM-bound row kernels of the other stream co-reside with this kernel.
 template <bool DUMP>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
-rvq_gemm_top4_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, Dp], box 64 x 128, SWIZZLE_128B
+rvq_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, Dp], box 64 x 128, SWIZZLE_128B
                      const __grid_constant__ CUtensorMap map_b,   // fp16 [L*Kp, Dp], box 64 x 256, SWIZZLE_128B
                      int n_rows, int n_tiles, int n_chunks, int n_kblocks, int b_row0,
                      const float4* __restrict__ rowinfo,          // per frame {alpha, bias, window, -}
@@ -142,14 +153,17 @@ rvq_gemm_top4_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows,
                 alpha = ri.x;
                 bias = ri.y;
             }
-            int gk0 = KEY_INVALID, gk1 = KEY_INVALID, gk2 = KEY_INVALID, gk3 = KEY_INVALID;
-            int gi0 = 0, gi1 = 0, gi2 = 0, gi3 = 0;
+            int gk[NCAND], gi[NCAND];
+#pragma unroll
+            for (int i = 0; i < NCAND; ++i) { gk[i] = KEY_INVALID; gi[i] = 0; }
             for (int chunk = 0; chunk < n_chunks; ++chunk, ++it) {
                 const uint32_t as = it & 1, aph = (it >> 1) & 1;
                 mbar_wait(&tfull[as], aph);
                 tcgen05_fence_after();
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N;
-                int k0 = KEY_INVALID, k1 = KEY_INVALID, k2 = KEY_INVALID, k3 = KEY_INVALID;
+                int lk[NCAND];
+#pragma unroll
+                for (int i = 0; i < NCAND; ++i) lk[i] = KEY_INVALID;
                 const float4* cn4 = reinterpret_cast<const float4*>(cn + chunk * BLOCK_N);
 #pragma unroll
                 for (int g = 0; g < BLOCK_N / 32; ++g) {
@@ -172,7 +186,7 @@ rvq_gemm_top4_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows,
                                 const int col = g * 32 + j4 * 4 + e;
                                 const float s = fmaf(__uint_as_float(v[j4 * 4 + e]), alpha, cc[e]) + bias;
                                 const int key = (__float_as_int(s) & 0xFFFFFF00) | col;
-                                top4_insert(key, k0, k1, k2, k3);
+                                topk_insert(key, lk);
                             }
                         }
                     }
@@ -182,27 +196,28 @@ rvq_gemm_top4_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows,
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[as]);
 
-                if (!DUMP) {   // merge the chunk's four keys into the running global four (stable: earlier chunk wins ties)
-                    const int lk[4] = {k0, k1, k2, k3};
+                if (!DUMP) {   // merge the chunk's keys into the running global list (stable: earlier chunk wins ties)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
+                    for (int i = 0; i < NCAND; ++i) {
                         int key = lk[i];
                         int idx = chunk * BLOCK_N + (key & 0xFF);
-                        bool lt;
-                        int tk, ti;
-                        lt = key < gk0; tk = gk0; ti = gi0; gk0 = lt ? key : gk0; gi0 = lt ? idx : gi0; key = lt ? tk : key; idx = lt ? ti : idx;
-                        lt = key < gk1; tk = gk1; ti = gi1; gk1 = lt ? key : gk1; gi1 = lt ? idx : gi1; key = lt ? tk : key; idx = lt ? ti : idx;
-                        lt = key < gk2; tk = gk2; ti = gi2; gk2 = lt ? key : gk2; gi2 = lt ? idx : gi2; key = lt ? tk : key; idx = lt ? ti : idx;
-                        lt = key < gk3;                     gk3 = lt ? key : gk3; gi3 = lt ? idx : gi3;
+#pragma unroll
+                        for (int p = 0; p < NCAND; ++p) {
+                            const bool lt = key < gk[p];
+                            const int tk = gk[p], ti = gi[p];
+                            gk[p] = lt ? key : tk;
+                            gi[p] = lt ? idx : ti;
+                            key = lt ? tk : key;
+                            idx = lt ? ti : idx;
+                        }
                     }
                 }
             }
             if (!DUMP && row < n_rows) {
                 Cand c;
-                c.key[0] = gk0; c.key[1] = gk1; c.key[2] = gk2; c.key[3] = gk3;
-                c.idx01 = static_cast<uint32_t>(gi0) | (static_cast<uint32_t>(gi1) << 16);
-                c.idx23 = static_cast<uint32_t>(gi2) | (static_cast<uint32_t>(gi3) << 16);
-                c.pad0 = 0; c.pad1 = 0;
+#pragma unroll
+                for (int i = 0; i < NCAND; ++i) { c.key[i] = gk[i]; c.idx[i] = static_cast<unsigned short>(gi[i]); }
+                c.pad[0] = c.pad[1] = c.pad[2] = 0;
                 cand[row] = c;
             }
         }

@@ -8,9 +8,9 @@
 //   mse = mean(t^2); loss = mse + w * mse  nat.py:2162-2164
 //   out = sum_l q_ste_l  (left to right)   nat.py:1408
 //
-// Exactness contract: the tensor-core pass yields, per frame, the four smallest packed scores. A frame
+// Exactness contract: the tensor-core pass yields, per frame, the six smallest packed scores. A frame
 // is decided from them only if the proven error window excludes every code that is not a candidate; candidates
-// inside the window are re-ranked with fp64 dot products on the fp32 data; frames whose fourth candidate is still
+// inside the window are re-ranked with fp64 dot products on the fp32 data; frames whose last candidate is still
 // inside the window take the exact full scan. Ties go to the lower index, as torch.argmin does (nat.py:2157).
 #pragma once
 
@@ -316,23 +316,22 @@ decide_update_kernel(UpdateArgs p, const gemm::Cand* __restrict__ cand, int* __r
     for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < p.n; row += warps) {
         const gemm::Cand c = cand[row];
         const float window = p.rowinfo[row].z;
-        const int idx[4] = {static_cast<int>(c.idx01 & 0xFFFF), static_cast<int>(c.idx01 >> 16),
-                            static_cast<int>(c.idx23 & 0xFFFF), static_cast<int>(c.idx23 >> 16)};
-        float f[4];
-        bool valid[4];
+        constexpr int NC = gemm::NCAND;
+        float f[NC];
+        bool valid[NC];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < NC; ++i) {
             f[i] = __int_as_float(c.key[i] & 0xFFFFFF00);
-            valid[i] = c.key[i] != gemm::KEY_INVALID && idx[i] < p.K && fabsf(f[i]) < 3.0e38f;
+            valid[i] = c.key[i] != gemm::KEY_INVALID && c.idx[i] < p.K && fabsf(f[i]) < 3.0e38f;
         }
         // 8 low bits of every key were replaced by the column: true shifted score lies in [f, f + |f| 2^-15].
         const float thr = f[0] + fabsf(f[0]) * 6.103515625e-05f + window;
         int nwin = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) nwin += (valid[i] && f[i] <= thr) ? 1 : 0;
-        int j = idx[0];
-        if (!valid[0] || (nwin == 4 && p.K > 4)) {
-            // the fourth candidate is still inside the window: codes we did not keep may matter -> exact full scan
+        for (int i = 0; i < NC; ++i) nwin += (valid[i] && f[i] <= thr) ? 1 : 0;
+        int j = c.idx[0];
+        if (!valid[0] || (nwin == NC && p.K > NC)) {
+            // the last kept candidate is still inside the window: codes we did not keep may matter -> exact full scan
             if (lane == 0) scan_list[atomicAdd(scan_count, 1)] = row;
             ++n_scan;
             continue;
@@ -342,9 +341,9 @@ decide_update_kernel(UpdateArgs p, const gemm::Cand* __restrict__ cand, int* __r
             double best = 0.0;
             int bestj = -1;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < NC; ++i) {
                 if (!(valid[i] && f[i] <= thr)) continue;          // warp-uniform
-                const int k = idx[i];
+                const int k = c.idx[i];
                 const double s = exact_score(r4, reinterpret_cast<const float4*>(p.cb + static_cast<long long>(k) * p.dp),
                                              dp4, p.cn64[k]);
                 if (bestj < 0 || s < best || (s == best && k < bestj)) { best = s; bestj = k; }
