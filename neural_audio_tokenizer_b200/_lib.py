@@ -9,7 +9,7 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libnat_b200.so")
+LIB_PATH = os.environ.get("NAT_B200_LIB") or os.path.join(_PKG_DIR, "libnat_b200.so")   # override: A/B builds
 
 NAT_OK = 0
 LAYOUT_BCT, LAYOUT_ROWS = 0, 1

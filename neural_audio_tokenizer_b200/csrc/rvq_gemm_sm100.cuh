@@ -32,16 +32,21 @@ constexpr int KEY_INVALID = 0x7FFFFFFF;
 // Candidates kept per frame. With the fp16 window about 1/6 of the score spacing at the minimum (randn data), the
 // chance that the last kept candidate is still inside the window falls ~6x per extra candidate: 4 -> 1e-3 of the
 // frames need the exact full scan, 6 -> 1e-6. Each candidate costs two integer min/max per score in the epilogue.
-constexpr int NCAND = 6;
+#ifndef NAT_NCAND
+#define NAT_NCAND 6
+#endif
+constexpr int NCAND = NAT_NCAND;
+#ifndef NAT_GEMM_MINBLOCKS
+#define NAT_GEMM_MINBLOCKS 1
+#endif
 
 // Candidates of one frame after the coarse pass: keys ascending; key = (score bits & ~0xFF) | column-in-chunk,
-// idx = global code index (16 bit). 48 bytes = three 16-byte stores.
+// idx = global code index (16 bit). The alignment pads the struct to a multiple of 16 bytes (48 for six).
 struct __align__(16) Cand {
     int key[NCAND];
     unsigned short idx[NCAND];
-    uint32_t pad[3];
 };
-static_assert(sizeof(Cand) == 48, "Cand layout");
+static_assert(sizeof(Cand) % 16 == 0, "Cand layout");
 
 // Branch-free insertion of v into the ascending list m[0..NCAND): 2*NCAND-1 integer min/max.
 __device__ __forceinline__ void topk_insert(int v, int (&m)[NCAND]) {
@@ -55,10 +60,10 @@ __device__ __forceinline__ void topk_insert(int v, int (&m)[NCAND]) {
 }
 
 // DUMP=true writes the raw accumulators instead of candidates (validation of the MMA path, tests only).
-// minBlocks = 2 only caps registers at 168 per thread (shared memory still admits one CTA per SM): the freed
-// register file lets the HBM-bound row kernels of the other stream co-reside with this kernel.
+// NAT_GEMM_MINBLOCKS = 2 would only cap registers at 168 per thread (shared memory still admits one CTA per SM) so
+// that row kernels of another stream can co-reside; measured slower on B200, default 1.
 template <bool DUMP>
-__global__ void __launch_bounds__(NUM_THREADS, 2)
+__global__ void __launch_bounds__(NUM_THREADS, NAT_GEMM_MINBLOCKS)
 rvq_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, Dp], box 64 x 128, SWIZZLE_128B
                      const __grid_constant__ CUtensorMap map_b,   // fp16 [L*Kp, Dp], box 64 x 256, SWIZZLE_128B
                      int n_rows, int n_tiles, int n_chunks, int n_kblocks, int b_row0,
@@ -217,7 +222,6 @@ rvq_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows,
                 Cand c;
 #pragma unroll
                 for (int i = 0; i < NCAND; ++i) { c.key[i] = gk[i]; c.idx[i] = static_cast<unsigned short>(gi[i]); }
-                c.pad[0] = c.pad[1] = c.pad[2] = 0;
                 cand[row] = c;
             }
         }
