@@ -279,7 +279,9 @@ def main():
                 prof_sum[k] += prof[k]
     gemm_launches = prof_sum[6]
     gemm_ms_per_launch = prof_sum[1] / max(gemm_launches, 1)
-    flops_per_launch = 2.0 * CODEBOOK * DIM * n_local             # one layer over all frames of this GPU
+    fused = os.environ.get("NAT_RVQ_FUSED", "1") != "0"
+    # fused: one launch = all 4 layers of a stack; per-layer kernels: one launch = one layer
+    flops_per_launch = 2.0 * CODEBOOK * DIM * n_local * (LAYERS_PER_STACK if fused else 1)
     achieved = flops_per_launch / (gemm_ms_per_launch * 1e-3) / 1e12
     peaks = measured_peaks()
     kernel_ms = {name: prof_sum[k] / prof_reps for k, name in enumerate(_lib.PROF_NAMES) if k < 6}
@@ -314,7 +316,8 @@ def main():
         "clocks": clocks.summary(),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
-                     "kernel": "rvq_gemm_topk_kernel", "peak_kind": f"{peaks['source']} sustained bf16 (kernel timed "
+                     "kernel": "rvq_stack_kernel (4 layers per launch: tcgen05 GEMM + candidates + exact decision + "
+                               "residual update)" if fused else "rvq_gemm_topk_kernel", "peak_kind": f"{peaks['source']} sustained bf16 (kernel timed "
                      "inside the step)", "frac_of_burst": achieved / peaks["bf16_tflops"],
                      "ms_per_launch": gemm_ms_per_launch, "flop_per_launch": flops_per_launch,
                      "kernel_ms_per_step": kernel_ms},

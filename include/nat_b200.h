@@ -167,6 +167,12 @@ int nat_debug_rvq_scores(const nat_rvq_codebooks* cb, int layer, const float* ro
                          float* scores_out_dev, float* row_scale_out_dev, float* cb_scale_out_dev,
                          void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* Per-CTA cycle counters of the fused stack kernel (where each warp role waits; rvq_stack_sm100.cuh DBG_*).
+ * enable != 0 switches recording on for later encode calls on this handle; out_host (optional) receives the counters
+ * of the launches since the last read, [min(max_ctas, n_ctas)][n_slots] uint64, and resets them. Synchronises. */
+int nat_debug_stack_counters(nat_rvq_codebooks* cb, int enable, unsigned long long* out_host, int max_ctas,
+                             int* n_ctas, int* n_slots);
+
 #ifdef __cplusplus
 }
 #endif

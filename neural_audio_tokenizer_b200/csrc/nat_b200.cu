@@ -23,6 +23,7 @@
 #include "rvq_gemm_sm100.cuh"
 #include "rvq_prepare.cuh"
 #include "rvq_rows.cuh"
+#include "rvq_stack_sm100.cuh"
 
 namespace {
 
@@ -120,8 +121,9 @@ struct Workspace {
     float* r;
     __half* a;
     float4* rowinfo;
+    float* rowamax;
     nat::gemm::Cand* cand;
-    double* row_loss;
+    double* row_loss;     // [L][rows]
     int* scan_list;
     int* scan_count;      // [L]
     double* loss_acc;     // [L]
@@ -130,11 +132,11 @@ struct Workspace {
 
 constexpr size_t kWsFixed = 4096;
 
-size_t ws_per_row(int dp) { return static_cast<size_t>(dp) * 6 + 16 + sizeof(nat::gemm::Cand) + 8 + 4; }
+size_t ws_per_row(int dp, int L) { return static_cast<size_t>(dp) * 6 + 16 + 4 + sizeof(nat::gemm::Cand) + 8 * L + 4; }
 
-bool carve(void* base, size_t bytes, int dp, long long want_rows, Workspace* ws) {
-    if (bytes <= kWsFixed + 256 * 8) return false;
-    long long rows = static_cast<long long>((bytes - kWsFixed - 256 * 8) / ws_per_row(dp));
+bool carve(void* base, size_t bytes, int dp, int L, long long want_rows, Workspace* ws) {
+    if (bytes <= kWsFixed + 256 * 9) return false;
+    long long rows = static_cast<long long>((bytes - kWsFixed - 256 * 9) / ws_per_row(dp, L));
     rows = std::min(rows, round_up(want_rows, 128));
     rows = rows / 128 * 128;
     if (rows < 128) return false;
@@ -145,8 +147,9 @@ bool carve(void* base, size_t bytes, int dp, long long want_rows, Workspace* ws)
     ws->r = reinterpret_cast<float*>(take(static_cast<size_t>(rows) * dp * 4));
     ws->a = reinterpret_cast<__half*>(take(static_cast<size_t>(rows) * dp * 2));
     ws->rowinfo = reinterpret_cast<float4*>(take(static_cast<size_t>(rows) * 16));
+    ws->rowamax = reinterpret_cast<float*>(take(static_cast<size_t>(rows) * 4));
     ws->cand = reinterpret_cast<nat::gemm::Cand*>(take(static_cast<size_t>(rows) * sizeof(nat::gemm::Cand)));
-    ws->row_loss = reinterpret_cast<double*>(take(static_cast<size_t>(rows) * 8));
+    ws->row_loss = reinterpret_cast<double*>(take(static_cast<size_t>(rows) * 8 * L));
     ws->scan_list = reinterpret_cast<int*>(take(static_cast<size_t>(rows) * 4));
     ws->rows = rows;
     return static_cast<size_t>(p - static_cast<char*>(base)) <= bytes;
@@ -163,6 +166,8 @@ struct nat_rvq_codebooks {
     nat::rows::LayerConst* lc;        // [L]
     int* scratch;                     // [L, kScratchPerLayer]
     CUtensorMap map_b;
+    unsigned long long* stack_dbg;    // [sm_count][DBG_SLOTS] cycle counters of the last fused launch (debug hook)
+    bool stack_dbg_on;
     // staging arena of the host-buffer entry point (grown on first use)
     void* host_arena_dev;
     size_t host_arena_bytes;
@@ -248,6 +253,14 @@ int nat_rvq_codebooks_create(const float* const* codebooks_dev, int L, int K, in
                                    nat::gemm::SMEM_BYTES), "cudaFuncSetAttribute");
         guard(cudaFuncSetAttribute(nat::gemm::rvq_gemm_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    nat::gemm::SMEM_BYTES), "cudaFuncSetAttribute");
+        guard(cudaFuncSetAttribute(nat::stack::rvq_stack_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   nat::stack::SMEM_BYTES), "cudaFuncSetAttribute");
+        guard(cudaFuncSetAttribute(nat::stack::rvq_stack_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   nat::stack::SMEM_BYTES), "cudaFuncSetAttribute");
+        guard(cudaFuncSetAttribute(nat::stack::rvq_stack_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   nat::stack::SMEM_BYTES), "cudaFuncSetAttribute");
+        guard(cudaFuncSetAttribute(nat::stack::rvq_stack_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   nat::stack::SMEM_BYTES), "cudaFuncSetAttribute");
         guard(cudaFuncSetAttribute(nat::rows::prep_bct_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    200 * 1024), "cudaFuncSetAttribute");
     }
@@ -267,7 +280,7 @@ int nat_rvq_codebooks_update(nat_rvq_codebooks* cb, const float* const* codebook
 int nat_rvq_codebooks_destroy(nat_rvq_codebooks* cb) {
     if (cb == nullptr) return NAT_OK;
     cudaFree(cb->cbf); cudaFree(cb->cbh); cudaFree(cb->cn32); cudaFree(cb->cn64); cudaFree(cb->lc);
-    cudaFree(cb->scratch); cudaFree(cb->host_arena_dev);
+    cudaFree(cb->scratch); cudaFree(cb->host_arena_dev); cudaFree(cb->stack_dbg);
     if (cb->copy_stream) cudaStreamDestroy(cb->copy_stream);
     for (auto& e : cb->ev) if (e) cudaEventDestroy(e);
     for (auto& s2 : cb->side) if (s2) cudaStreamDestroy(s2);
@@ -285,10 +298,10 @@ int nat_rvq_codebooks_dims(const nat_rvq_codebooks* cb, int* L, int* K, int* D) 
 }
 
 size_t nat_rvq_workspace_bytes(const nat_rvq_codebooks* cb, int64_t n_frames) {
-    if (cb == nullptr || n_frames <= 0) return kWsFixed + 256 * 8 + 128 * ws_per_row(64);
+    if (cb == nullptr || n_frames <= 0) return kWsFixed + 256 * 9 + 128 * ws_per_row(64, 16);
     // two lanes, each holding half of the frames rounded up to a tile (see nat_rvq_encode_f32)
     const long long per_lane = std::min<long long>(round_up((n_frames + 1) / 2, 128), chunk_cap_rows() / 2);
-    const size_t lane_bytes = static_cast<size_t>(round_up(kWsFixed + 256 * 8 + per_lane * ws_per_row(cb->dp), 256));
+    const size_t lane_bytes = static_cast<size_t>(round_up(kWsFixed + 256 * 9 + per_lane * ws_per_row(cb->dp, cb->L), 256));
     return 2 * lane_bytes;
 }
 
@@ -299,21 +312,31 @@ static int launch_layer0_prep(const nat_rvq_codebooks* cb, const Workspace& ws, 
     const int warps_grid = std::min((n + 7) / 8, cb->sm_count * 16);
     if (layout == NAT_LAYOUT_ROWS) {
         NAT_LAUNCH(0, st, rows::prep_rows_kernel<<<warps_grid, 256, 0, st>>>(x + n0 * cb->D, cb->D, n, cb->D, cb->dp, ws.r, ws.a,
-                                                           ws.rowinfo, cb->lc, false));
+                                                           ws.rowinfo, ws.rowamax, cb->lc, false));
     } else {
         const size_t smem = static_cast<size_t>(rows::kPrepFrames) * (cb->dp + 1) * sizeof(float);
         if (smem <= 200 * 1024) {
             NAT_LAUNCH(0, st, rows::prep_bct_fused_kernel<<<(n + rows::kPrepFrames - 1) / rows::kPrepFrames, 256, smem, st>>>(
-                x, T, cb->D, n0, n, cb->dp, ws.r, ws.a, ws.rowinfo, cb->lc));
+                x, T, cb->D, n0, n, cb->dp, ws.r, ws.a, ws.rowinfo, ws.rowamax, cb->lc));
         } else {
             dim3 grid((n + 31) / 32, cb->dp / 32);
             NAT_LAUNCH(0, st, rows::bct_to_rows_kernel<<<grid, 256, 0, st>>>(x, T, cb->D, n0, n, cb->dp, ws.r));
             NAT_LAUNCH(0, st, rows::prep_rows_kernel<<<warps_grid, 256, 0, st>>>(nullptr, 0, n, cb->D, cb->dp, ws.r, ws.a,
-                                                                              ws.rowinfo, cb->lc, true));
+                                                                              ws.rowinfo, ws.rowamax, cb->lc, true));
         }
     }
     NAT_CUDA(cudaGetLastError());
     return NAT_OK;
+}
+
+static bool fused_enabled() {
+    const char* e = getenv("NAT_RVQ_FUSED");         // read every call: tests flip it to cross-check both paths
+    return e == nullptr || atoi(e) != 0;
+}
+static int fused_group() {
+    const char* e = getenv("NAT_RVQ_GROUP");
+    const int v = e ? atoi(e) : 0;
+    return v >= 1 ? v : 2;
 }
 
 // Everything one chunk of frames [n0, n0 + n) needs, in order, on one stream.
@@ -332,9 +355,37 @@ static int encode_chunk(const EncodeCall& c, const Workspace& ws, const CUtensor
     if (int rc = launch_layer0_prep(cb, ws, c.x, c.layout, c.T, n0, n, st)) return rc;
     NAT_CUDA(cudaMemsetAsync(ws.scan_count, 0, sizeof(int) * cb->L, st));
     const int n_tiles = (n + gemm::BLOCK_M - 1) / gemm::BLOCK_M;
+    if (!c.exact && fused_enabled() && cb->dp <= 1024) {
+        // one persistent launch for all L layers (rvq_stack_sm100.cuh)
+        stack::StackArgs sa;
+        sa.cbf = cb->cbf; sa.cn64 = cb->cn64; sa.cn32 = cb->cn32; sa.lc = cb->lc;
+        sa.r = ws.r; sa.a = ws.a; sa.rowinfo = ws.rowinfo; sa.rowamax = ws.rowamax;
+        sa.codes = c.codes; sa.codes_ld = c.N; sa.code_off = n0;
+        sa.row_loss = c.want_loss ? ws.row_loss : nullptr; sa.loss_ld = ws.rows;
+        sa.stats = c.stats;
+        sa.n_rows = n; sa.n_tiles = n_tiles; sa.L = cb->L; sa.K = cb->K; sa.kp = cb->kp; sa.dp = cb->dp;
+        sa.code_dtype = c.code_dtype;
+        sa.group = fused_group();
+        sa.dbg = cb->stack_dbg_on ? cb->stack_dbg : nullptr;
+        { const char* e = getenv("NAT_RVQ_DBG_MODE"); sa.dbg_mode = e ? atoi(e) : 0; }
+        const int grid = std::min(n_tiles, cb->sm_count);
+        const int nv = (cb->dp / 4 + 31) / 32;
+        NAT_LAUNCH(1, st, {
+            if (nv <= 2) stack::rvq_stack_kernel<2><<<grid, stack::NUM_THREADS, stack::SMEM_BYTES, st>>>(map_a, cb->map_b, sa);
+            else if (nv <= 4) stack::rvq_stack_kernel<4><<<grid, stack::NUM_THREADS, stack::SMEM_BYTES, st>>>(map_a, cb->map_b, sa);
+            else if (nv <= 6) stack::rvq_stack_kernel<6><<<grid, stack::NUM_THREADS, stack::SMEM_BYTES, st>>>(map_a, cb->map_b, sa);
+            else stack::rvq_stack_kernel<8><<<grid, stack::NUM_THREADS, stack::SMEM_BYTES, st>>>(map_a, cb->map_b, sa);
+        });
+        NAT_CUDA(cudaGetLastError());
+        if (c.want_loss)
+            for (int l = 0; l < cb->L; ++l)
+                NAT_LAUNCH(4, st, rows::reduce_loss_kernel<<<1, 1024, 0, st>>>(ws.row_loss + static_cast<long long>(l) * ws.rows,
+                                                                              n, ws.loss_acc + l));
+        NAT_CUDA(cudaGetLastError());
+    } else
     for (int l = 0; l < cb->L; ++l) {
         rows::UpdateArgs ua;
-        ua.r = ws.r; ua.a = ws.a; ua.rowinfo = ws.rowinfo;
+        ua.r = ws.r; ua.a = ws.a; ua.rowinfo = ws.rowinfo; ua.rowamax = ws.rowamax;
         ua.cb = cb->cbf + l * cb_layer_ld;
         ua.cn64 = cb->cn64 + static_cast<long long>(l) * cb->K;
         ua.lc_next = (l + 1 < cb->L) ? cb->lc + l + 1 : nullptr;
@@ -365,7 +416,7 @@ static int encode_chunk(const EncodeCall& c, const Workspace& ws, const CUtensor
         const int warps_grid = std::min((n + 7) / 8, cb->sm_count * 16);
         if (c.layout == NAT_LAYOUT_ROWS) {
             NAT_LAUNCH(0, st, rows::prep_rows_kernel<<<warps_grid, 256, 0, st>>>(c.x + n0 * cb->D, cb->D, n, cb->D, cb->dp,
-                                                                              ws.r, ws.a, ws.rowinfo, cb->lc, false));
+                                                                              ws.r, ws.a, ws.rowinfo, ws.rowamax, cb->lc, false));
         } else {
             dim3 grid((n + 31) / 32, cb->dp / 32);
             NAT_LAUNCH(0, st, rows::bct_to_rows_kernel<<<grid, 256, 0, st>>>(c.x, c.T, cb->D, n0, n, cb->dp, ws.r));
@@ -419,7 +470,7 @@ int nat_rvq_encode_f32(const nat_rvq_codebooks* cb_const, const float* x_dev, in
     const size_t half_bytes = (workspace_bytes / n_lanes) & ~static_cast<size_t>(255);
     const long long want = std::min<long long>((N + n_lanes - 1) / n_lanes, chunk_cap_rows());
     for (int i = 0; i < n_lanes; ++i) {
-        if (!carve(static_cast<char*>(workspace_dev) + i * half_bytes, half_bytes, cb->dp, want, &ws[i]))
+        if (!carve(static_cast<char*>(workspace_dev) + i * half_bytes, half_bytes, cb->dp, cb->L, want, &ws[i]))
             return fail(NAT_ERR_WORKSPACE, "workspace of %zu bytes cannot hold one 128-frame tile per lane (need %zu)",
                         workspace_bytes, nat_rvq_workspace_bytes(cb, 128 * n_lanes));
         if (int rc = make_map_f16(&map_a[i], ws[i].a, ws[i].rows, cb->dp, 128)) return rc;
@@ -509,6 +560,27 @@ int nat_rvq_decode_f32(const nat_rvq_codebooks* cb, const void* codes_dev, int c
     return NAT_OK;
 }
 
+int nat_debug_stack_counters(nat_rvq_codebooks* cb, int enable, unsigned long long* out_host, int max_ctas,
+                              int* n_ctas, int* n_slots) {
+    if (cb == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null handle");
+    const size_t bytes = sizeof(unsigned long long) * cb->sm_count * nat::stack::DBG_SLOTS;
+    if (cb->stack_dbg == nullptr) {
+        NAT_CUDA(cudaMalloc(&cb->stack_dbg, bytes));
+        NAT_CUDA(cudaMemset(cb->stack_dbg, 0, bytes));
+    }
+    if (out_host != nullptr) {
+        NAT_CUDA(cudaDeviceSynchronize());                     // debug hook, not a hot path
+        const int n = std::min(max_ctas, cb->sm_count);
+        NAT_CUDA(cudaMemcpy(out_host, cb->stack_dbg, sizeof(unsigned long long) * n * nat::stack::DBG_SLOTS,
+                            cudaMemcpyDeviceToHost));
+        NAT_CUDA(cudaMemset(cb->stack_dbg, 0, bytes));
+    }
+    cb->stack_dbg_on = enable != 0;
+    if (n_ctas) *n_ctas = cb->sm_count;
+    if (n_slots) *n_slots = nat::stack::DBG_SLOTS;
+    return NAT_OK;
+}
+
 int nat_debug_rvq_scores(const nat_rvq_codebooks* cb, int layer, const float* rows_dev, int64_t N,
                          float* scores_out_dev, float* row_scale_out_dev, float* cb_scale_out_dev,
                          void* workspace_dev, size_t workspace_bytes, void* stream) {
@@ -518,14 +590,14 @@ int nat_debug_rvq_scores(const nat_rvq_codebooks* cb, int layer, const float* ro
     if (layer < 0 || layer >= cb->L) return fail(NAT_ERR_INVALID_ARGUMENT, "layer out of range");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Workspace ws;
-    if (!carve(workspace_dev, workspace_bytes, cb->dp, N, &ws) || ws.rows < N)
+    if (!carve(workspace_dev, workspace_bytes, cb->dp, cb->L, N, &ws) || ws.rows < N)
         return fail(NAT_ERR_WORKSPACE, "debug call needs a workspace for all %lld rows", (long long)N);
     CUtensorMap map_a;
     if (int rc = make_map_f16(&map_a, ws.a, ws.rows, cb->dp, 128)) return rc;
     const int n = static_cast<int>(N);
     if (cb->dp != cb->D) NAT_CUDA(cudaMemsetAsync(ws.a, 0, static_cast<size_t>(ws.rows) * cb->dp * 2, st));
     NAT_LAUNCH(0, st, rows::prep_rows_kernel<<<std::min((n + 7) / 8, cb->sm_count * 16), 256, 0, st>>>(
-        rows_dev, cb->D, n, cb->D, cb->dp, ws.r, ws.a, ws.rowinfo, cb->lc + layer, false));
+        rows_dev, cb->D, n, cb->D, cb->dp, ws.r, ws.a, ws.rowinfo, ws.rowamax, cb->lc + layer, false));
     const int n_tiles = (n + gemm::BLOCK_M - 1) / gemm::BLOCK_M;
     NAT_LAUNCH(1, st, gemm::rvq_gemm_topk_kernel<true><<<std::min(n_tiles, cb->sm_count), gemm::NUM_THREADS, gemm::SMEM_BYTES, st>>>(
         map_a, cb->map_b, n, n_tiles, cb->kp / gemm::BLOCK_N, cb->dp / gemm::BLOCK_K, layer * cb->kp, ws.rowinfo,

@@ -79,7 +79,8 @@ __global__ void finish_consts_kernel(const int* __restrict__ scratch, int L, row
     c.clo_max = sqrtf(__int_as_float(s[2])) * up;
     c.ctil_max = sqrtf(__int_as_float(s[3])) * up;
     c.cmax2 = __int_as_float(s[4]);
-    c.pad[0] = c.pad[1] = c.pad[2] = 0.f;
+    c.cabs = __int_as_float(s[0]);
+    c.pad[0] = c.pad[1] = 0.f;
     lc[l] = c;
 }
 

@@ -27,7 +27,8 @@ struct LayerConst {
     float clo_max;     // max_k ||c_hat_k - fp16(c_hat_k)||
     float ctil_max;    // max_k ||fp16(c_hat_k)||
     float cmax2;       // max_k ||c_k||^2  (unscaled)
-    float pad[3];
+    float cabs;        // max |c_kd|       (unscaled): bounds the growth of a residual row's largest element
+    float pad[2];
 };
 
 constexpr float kGammaPerK = 2.384185791015625e-07f;   // 2^-22 per accumulated product: tensor-core fp32 accumulation
@@ -61,13 +62,23 @@ __device__ __forceinline__ float4 make_rowinfo(float sx, float lo2, float xt2, f
     return ri;
 }
 
+// Same triple when only ||x_hat||^2 and ||x_hat - fp16(x_hat)||^2 were summed: ||fp16(x_hat)|| <= ||x_hat|| + ||lo||.
+__device__ __forceinline__ float4 make_rowinfo_bound(float sx, float lo2, float xh2, const LayerConst* __restrict__ lc,
+                                                     int d_pad) {
+    const float up = 1.0005f;
+    const float xt = (sqrtf(xh2 * up) + sqrtf(lo2 * up)) * 1.000001f;
+    return make_rowinfo(sx, lo2, xt * xt, xh2, lc, d_pad);
+}
+
 // Second half of every row producer: given the fp32 row already in global memory, emit the fp16 operand row and the
 // {alpha, bias, window} triple the coarse pass and the decision need. Warp-collective.
 __device__ __forceinline__ void finalize_row(const float4* r4, int dp4, float amax_lane,
                                              uint2* __restrict__ a_row, float4* __restrict__ rowinfo_out,
-                                             const LayerConst* __restrict__ lc, int d_pad) {
+                                             const LayerConst* __restrict__ lc, int d_pad,
+                                             float* __restrict__ rowamax_out) {
     const int lane = threadIdx.x & 31;
     const float amax = warp_max(amax_lane);
+    if (lane == 0 && rowamax_out != nullptr) *rowamax_out = amax;
     const float sx = pow2_scale_for(amax);
     float lo2 = 0.f, xt2 = 0.f, xh2 = 0.f;
     for (int i = lane; i < dp4; i += 32) {
@@ -98,8 +109,8 @@ __device__ __forceinline__ void finalize_row(const float4* r4, int dp4, float am
 // x rows [n, D] (any alignment) -> r [n, Dp] fp32 (zero padded), A [n, Dp] fp16, rowinfo. One warp per frame.
 __global__ void __launch_bounds__(256)
 prep_rows_kernel(const float* __restrict__ x, long long x_ld, int n, int D, int dp, float* __restrict__ r,
-                 __half* __restrict__ a, float4* __restrict__ rowinfo, const LayerConst* __restrict__ lc,
-                 bool in_place) {
+                 __half* __restrict__ a, float4* __restrict__ rowinfo, float* __restrict__ rowamax,
+                 const LayerConst* __restrict__ lc, bool in_place) {
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
@@ -121,7 +132,8 @@ prep_rows_kernel(const float* __restrict__ x, long long x_ld, int n, int D, int 
             __syncwarp();
         }
         finalize_row(reinterpret_cast<const float4*>(rr), dp / 4, amax,
-                     reinterpret_cast<uint2*>(a + static_cast<long long>(row) * dp), rowinfo + row, lc, dp);
+                     reinterpret_cast<uint2*>(a + static_cast<long long>(row) * dp), rowinfo + row, lc, dp,
+                     rowamax != nullptr ? rowamax + row : nullptr);
     }
 }
 
@@ -132,7 +144,7 @@ constexpr int kPrepFrames = 32;
 __global__ void __launch_bounds__(256)
 prep_bct_fused_kernel(const float* __restrict__ x, long long T, int D, long long n0, int n, int dp,
                       float* __restrict__ r, __half* __restrict__ a, float4* __restrict__ rowinfo,
-                      const LayerConst* __restrict__ lc) {
+                      float* __restrict__ rowamax, const LayerConst* __restrict__ lc) {
     extern __shared__ float s_tile[];                   // [32][dp + 1]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ld = dp + 1;
@@ -180,7 +192,10 @@ prep_bct_fused_kernel(const float* __restrict__ x, long long T, int D, long long
             ar[i] = h;
         }
         lo2 = warp_sum(lo2); xt2 = warp_sum(xt2); xh2 = warp_sum(xh2);
-        if (lane == 0) rowinfo[row] = make_rowinfo(sx, lo2, xt2, xh2, lc, dp);
+        if (lane == 0) {
+            rowinfo[row] = make_rowinfo(sx, lo2, xt2, xh2, lc, dp);
+            if (rowamax != nullptr) rowamax[row] = amax;
+        }
     }
 }
 
@@ -260,6 +275,7 @@ struct UpdateArgs {
     float* r;                 // [n, Dp] residual, updated in place
     __half* a;                // [n, Dp] fp16 operand of the NEXT layer
     float4* rowinfo;          // per frame, read (this layer's window) then overwritten (next layer)
+    float* rowamax;           // per frame max |r| (kept current for the fused kernel's scale bound), or nullptr
     const float* cb;          // this layer's codebook [K, Dp] fp32 (zero padded)
     const double* cn64;       // [K] ||c_k||^2 in fp64
     const LayerConst* lc_next;   // constants of the next layer, nullptr on the last
@@ -301,7 +317,7 @@ __device__ __forceinline__ void apply_code(const UpdateArgs& p, int row, int j) 
     if (p.lc_next != nullptr) {
         __syncwarp();
         finalize_row(r4, dp4, amax, reinterpret_cast<uint2*>(p.a + static_cast<long long>(row) * p.dp),
-                     p.rowinfo + row, p.lc_next, p.dp);
+                     p.rowinfo + row, p.lc_next, p.dp, p.rowamax != nullptr ? p.rowamax + row : nullptr);
     }
 }
 

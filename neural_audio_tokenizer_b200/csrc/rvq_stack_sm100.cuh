@@ -1,0 +1,734 @@
+// One persistent sm_100a kernel for a whole RVQ stack: every layer's codebook search (tcgen05 GEMM, fp32
+// accumulators in TMEM), the exact decision, the residual update and the next layer's tensor-core operand.
+//
+// Replaces ResidualVectorQuantizer.forward's layer loop (nat.py:1398-1408) around VectorQuantizer.forward
+// (nat.py:2146-2167): cdist + argmin + gather + straight-through update, for all L layers of one stack, in one
+// launch. A CTA owns the 128-frame tiles  blockIdx.x, blockIdx.x + gridDim.x, ...  through ALL layers, so the
+// only cross-layer dependency (tile t of layer l+1 needs the update of tile t of layer l) stays inside the CTA and
+// is a shared-memory counter, not a grid-wide barrier or a kernel boundary.
+//
+// Order of work inside a CTA: its tiles are taken in groups of `group` tiles; inside a group the jobs run
+// layer-major  (t0,l0) (t1,l0) (t0,l1) (t1,l1) ...  so the update of one tile runs under the GEMM of the other(s)
+// and a tile's residual / operand rows are re-read a few microseconds after they were written, from L2.
+//
+// Warp roles (448 threads):
+//   warps 0..3    candidates: tcgen05.ld of the accumulators, coarse score, running-threshold candidate list
+//   warps 4..11   update: exact decision (fp64 re-rank where the window demands it), residual update in the
+//                 reference's op order, next-layer fp16 operand + error window, index streams
+//   warp 12       TMA producer (A tile 128 frames x 64, B tile 256 codes x 64 per K-block, 4-stage ring)
+//   warp 13       TMEM owner + single-thread tcgen05.mma issuer (two 256-column accumulator stages)
+//
+// Coarse pass and certificate (DESIGN.md "Exactness"): for frame n the kept set is every code whose coarse score
+// s_k = acc_k * alpha + ||c_k||^2 lies within the frame's proven window W of the running minimum; the final filter
+// against the final minimum leaves {k : s_k <= min_k s + W}, which must contain the true fp32-data argmin. One
+// survivor: certified. Several: exact fp64 re-rank. List overflow (adversarial orderings only): exact full scan by
+// the update warp. Ties go to the lowest index (nat.py:2157).
+#pragma once
+
+#include "nat_common.cuh"
+#include "rvq_rows.cuh"
+
+#ifndef NAT_REGS_EPI
+#define NAT_REGS_EPI 88
+#define NAT_REGS_UPD 88
+#endif
+
+namespace nat {
+namespace stack {
+
+constexpr int BLOCK_M = 128;     // frames per tile == TMEM lanes
+constexpr int BLOCK_N = 256;     // codes per accumulator stage
+constexpr int BLOCK_K = 64;      // fp16 elements per K-block == one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+constexpr int EPI_WARPS = 4;
+constexpr int UPD_WARPS = 16;
+constexpr int WARP_EPI0 = 0;
+constexpr int WARP_UPD0 = EPI_WARPS;
+constexpr int WARP_TMA = EPI_WARPS + UPD_WARPS;
+constexpr int WARP_MMA = WARP_TMA + 1;
+constexpr int NUM_THREADS = 768;  // six warpgroups: candidates | 4 x update | TMA, MMA and two idle warps
+// 80 registers per thread at launch; after setmaxnreg: 128 * (104 + 4 * 88 + 40) <= 64 K
+constexpr int REGS_EPI = NAT_REGS_EPI, REGS_UPD = NAT_REGS_UPD, REGS_AUX = 40;
+static_assert(WARP_MMA + 1 <= NUM_THREADS / 32 && EPI_WARPS == 4 && UPD_WARPS == 16, "warpgroup layout");
+static_assert(REGS_EPI + (UPD_WARPS / 4) * REGS_UPD + REGS_AUX <= 6 * 80, "setmaxnreg only moves registers inside the CTA: the total must not exceed the launch allocation");
+constexpr int TMEM_COLS = 2 * BLOCK_N;
+constexpr int ROWS_PER_UPD_WARP = BLOCK_M / UPD_WARPS;
+constexpr int LCAP = 16;         // eight-code groups listed per frame (compacted when full and at the end)
+constexpr int HCAP = 7;          // candidates handed to the update warps per frame
+constexpr unsigned HAND_SCAN = 0xFFFFu;
+
+constexpr int OFF_A = 0;
+constexpr int OFF_B = OFF_A + STAGES * A_STAGE_BYTES;
+constexpr int OFF_LIST_S = OFF_B + STAGES * B_STAGE_BYTES;
+constexpr int OFF_LIST_I = OFF_LIST_S + LCAP * BLOCK_M * 4;
+constexpr int OFF_HAND = OFF_LIST_I + LCAP * BLOCK_M * 4;
+constexpr int OFF_CN = OFF_HAND + 2 * BLOCK_M * 16;          // [2][BLOCK_N] ||c||^2 of the chunk being scored / the next
+constexpr int OFF_BARS = OFF_CN + 2 * BLOCK_N * 4;
+constexpr int SMEM_BYTES = OFF_BARS + 256 + 1024 /*alignment slack*/;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+
+struct StackArgs {
+    const float* cbf;            // [L, K, dp] fp32 codebooks, zero padded
+    const double* cn64;          // [L, K]
+    const float* cn32;           // [L, kp], +inf in the padding
+    const rows::LayerConst* lc;  // [L]
+    float* r;                    // [rows, dp] residual rows, layer-0 content written by the prep kernel
+    __half* a;                   // [rows, dp] fp16 operand rows, ditto
+    float4* rowinfo;             // [rows] {alpha, -, window, sx}, ditto
+    float* rowamax;              // [rows] max |r| of the row, ditto; kept current layer by layer
+    void* codes;                 // [L, codes_ld] index streams
+    long long codes_ld, code_off;
+    double* row_loss;            // [L, loss_ld] per-frame sum of t^2, or nullptr
+    long long loss_ld;
+    unsigned long long* stats;   // [L, 4] counters or nullptr
+    int n_rows, n_tiles, L, K, kp, dp, code_dtype;
+    int group;                   // tiles per group (>= 1); >= tiles per CTA means plain layer-major order
+    int dbg_mode;                // timing experiments only (results invalid when != 0)
+    unsigned long long* dbg;     // optional [grid][DBG_SLOTS] cycle counters (nat_debug_stack_counters), or nullptr
+};
+
+// Cycle counters per CTA when StackArgs::dbg is set: where each role waits.
+enum { DBG_TMA_WAIT_READY = 0, DBG_TMA_WAIT_EMPTY, DBG_MMA_WAIT_TEMPTY, DBG_MMA_WAIT_FULL, DBG_EPI_WAIT_TFULL,
+       DBG_EPI_WAIT_CEMPTY, DBG_EPI_TOTAL, DBG_UPD_WAIT_CFULL, DBG_UPD_TOTAL, DBG_KERNEL_TOTAL, DBG_EPI_WAIT_LD, DBG_EPI_EVENTS, DBG_UPD_DECIDE, DBG_UPD_RESID, DBG_UPD_FENCE, DBG_SLOTS = 16 };
+
+struct WaitClock {
+    long long acc = 0;
+    bool on;
+    __device__ explicit WaitClock(bool enabled) : on(enabled) {}
+    __device__ __forceinline__ long long begin() const { return on ? clock64() : 0; }
+    __device__ __forceinline__ void end(long long t0) { if (on) acc += clock64() - t0; }
+};
+
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void st_release(unsigned* smem_counter, unsigned v) {
+    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(smem_counter)), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* smem_counter) {
+    unsigned v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(smem_counter)) : "memory");
+    return v;
+}
+// Bounded like mbar_wait: a protocol bug must trap, not hang the GPU.
+__device__ __forceinline__ void wait_counter(const unsigned* smem_counter, unsigned need) {
+    if (ld_acquire(smem_counter) >= need) return;
+    const long long t0 = clock64();
+    while (ld_acquire(smem_counter) < need) {
+        __nanosleep(32);
+        if (clock64() - t0 > 4000000000LL) {
+            printf("nat_b200: update counter wait timed out (block %d, need %u, have %u)\n", blockIdx.x, need,
+                   ld_acquire(smem_counter));
+            __trap();
+        }
+    }
+}
+
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u16(uint32_t addr, unsigned short v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory"); }
+__device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f32x2(uint32_t addr, float2 v) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory"); }
+__device__ __forceinline__ void bar_sync_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ float lds_f32(uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
+
+// fp64 score ||c||^2 - 2 r.c of one code against the frame held in registers (lane-strided float4s). Same
+// accumulation order as rows::exact_score, so both device paths produce identical decisions.
+template <int NV>
+__device__ __forceinline__ double score_regs(const float4 (&rv)[NV], const float4* __restrict__ c4, int dp4,
+                                             double cn64, int lane) {
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int q = i * 32 + lane;
+        if (q < dp4) {
+            const float4 b = __ldcg(c4 + q);
+            acc = fma(static_cast<double>(rv[i].x), static_cast<double>(b.x), acc);
+            acc = fma(static_cast<double>(rv[i].y), static_cast<double>(b.y), acc);
+            acc = fma(static_cast<double>(rv[i].z), static_cast<double>(b.z), acc);
+            acc = fma(static_cast<double>(rv[i].w), static_cast<double>(b.w), acc);
+        }
+    }
+    acc = warp_sum(acc);
+    return cn64 - 2.0 * acc;
+}
+
+template <int NV>
+__device__ __forceinline__ void load_row(float4 (&rv)[NV], const float4* __restrict__ r4, int dp4, int lane) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int q = k * 32 + lane;
+        rv[k] = q < dp4 ? __ldcg(r4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+template <int NV>
+__device__ __forceinline__ void load_code(float4 (&cv)[NV], const float4* __restrict__ c4, int dp4, int lane) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int q = k * 32 + lane;
+        cv[k] = q < dp4 ? __ldcg(c4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+// a - b on both halves, rounded exactly like two __fsub_rn (one fused multiply by -1, one rounding)
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
+
+template <int NV>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp], box 64 x 128, SWIZZLE_128B
+                 const __grid_constant__ CUtensorMap map_b,   // fp16 [L*kp, dp], box 64 x 256, SWIZZLE_128B
+                 const __grid_constant__ StackArgs p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem + OFF_A;
+    uint8_t* smem_b = smem + OFF_B;
+    float* list_s = reinterpret_cast<float*>(smem + OFF_LIST_S);                    // [LCAP][128]
+    uint32_t* list_i = reinterpret_cast<uint32_t*>(smem + OFF_LIST_I);              // [LCAP][128] group id << 8 | mask
+    uint4* hand = reinterpret_cast<uint4*>(smem + OFF_HAND);                        // [2][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
+    uint64_t* full = bars;                  // TMA -> MMA
+    uint64_t* empty = bars + STAGES;        // MMA -> TMA
+    uint64_t* tfull = bars + 2 * STAGES;    // MMA -> candidates (accumulator stage ready)
+    uint64_t* tempty = tfull + 2;           // candidates -> MMA (accumulator stage drained)
+    uint64_t* cfull = tempty + 2;           // candidates -> update (hand-off slot written)
+    uint64_t* cempty = cfull + 2;           // update -> candidates (hand-off slot read)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cempty + 2);
+    unsigned* ready = tmem_slot + 1;        // [UPD_WARPS] jobs finished by each update warp
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_chunks = p.kp / BLOCK_N;
+    const int n_kblocks = p.dp / BLOCK_K;
+    const int my_tiles = (p.n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                         static_cast<int>(gridDim.x);
+    const int group = max(1, p.group);
+
+    if (warp == WARP_TMA && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull[i], 1);
+            mbar_init(&tempty[i], EPI_WARPS);
+            mbar_init(&cfull[i], EPI_WARPS);
+            mbar_init(&cempty[i], UPD_WARPS);
+        }
+        for (int i = 0; i < UPD_WARPS; ++i) ready[i] = 0;
+        fence_mbar_init();
+    } else if (warp == WARP_MMA) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // Registers follow the work: the update warps hold two residual rows and two code vectors in flight.
+    // (setmaxnreg sits at the top of each role's branch so that ptxas budgets the branch accordingly.)
+    // Every role walks the same job sequence:  for each group g0 .. : for each layer l : for each tile i of the group.
+    if (warp >= WARP_TMA) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_AUX));
+    if (warp == WARP_TMA) {
+        // ------------------------------------------------------------------ TMA producer (lane 0 issues)
+        uint32_t s = 0, ph = 0;
+        unsigned job = 0;
+        WaitClock w_ready(p.dbg != nullptr), w_empty(p.dbg != nullptr);
+        const long long t_start = w_ready.begin();
+        for (int g0 = 0; g0 < my_tiles; g0 += group) {
+            const int gs = min(group, my_tiles - g0);
+            for (int l = 0; l < p.L; ++l) {
+                for (int i = g0; i < g0 + gs; ++i, ++job) {
+                    const int tile = blockIdx.x + i * gridDim.x;
+                    if (l > 0) {
+                        const long long t0 = w_ready.begin();
+                        // operand rows of (tile, l) are written by this CTA's update warps in job (tile, l-1):
+                        // every update warp must have finished that job (they progress independently)
+                        if (lane < UPD_WARPS) wait_counter(&ready[lane], job - gs + 1);
+                        __syncwarp();
+                        fence_proxy_async();
+                        w_ready.end(t0);
+                    }
+                    if (lane == 0) {
+                        for (int chunk = 0; chunk < n_chunks; ++chunk) {
+                            for (int kb = 0; kb < n_kblocks; ++kb) {
+                                const long long t1 = w_empty.begin();
+                                mbar_wait(&empty[s], ph ^ 1);
+                                w_empty.end(t1);
+                                mbar_arrive_expect_tx(&full[s], A_STAGE_BYTES + B_STAGE_BYTES);
+                                tma_load_2d(smem_a + s * A_STAGE_BYTES, &map_a, &full[s], kb * BLOCK_K, tile * BLOCK_M);
+                                tma_load_2d(smem_b + s * B_STAGE_BYTES, &map_b, &full[s], kb * BLOCK_K,
+                                            l * p.kp + chunk * BLOCK_N);
+                                if (++s == STAGES) { s = 0; ph ^= 1; }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        if (p.dbg != nullptr && lane == 0) {
+            unsigned long long* d = p.dbg + static_cast<size_t>(blockIdx.x) * DBG_SLOTS;
+            d[DBG_TMA_WAIT_READY] = w_ready.acc;
+            d[DBG_TMA_WAIT_EMPTY] = w_empty.acc;
+            d[DBG_KERNEL_TOTAL] = clock64() - t_start;
+        }
+    } else if (warp == WARP_MMA) {
+        // ------------------------------------------------------------------ MMA issuer (one thread)
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16_f32(BLOCK_M, BLOCK_N);
+            uint32_t s = 0, ph = 0;
+            const int total = p.L * my_tiles * n_chunks;
+            WaitClock w_tempty(p.dbg != nullptr), w_full(p.dbg != nullptr);
+            for (int it = 0; it < total; ++it) {
+                const uint32_t as = it & 1, aph = (it >> 1) & 1;
+                const long long t0 = w_tempty.begin();
+                mbar_wait(&tempty[as], aph ^ 1);
+                w_tempty.end(t0);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+                for (int kb = 0; kb < n_kblocks; ++kb) {
+                    const long long t1 = w_full.begin();
+                    mbar_wait(&full[s], ph);
+                    w_full.end(t1);
+                    tcgen05_fence_after();
+                    const uint64_t adesc = umma_desc_kmajor_sw128(smem_a + s * A_STAGE_BYTES);
+                    const uint64_t bdesc = umma_desc_kmajor_sw128(smem_b + s * B_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                        umma_f16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    umma_commit(&empty[s]);
+                    if (kb == n_kblocks - 1) umma_commit(&tfull[as]);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+            if (p.dbg != nullptr) {
+                unsigned long long* d = p.dbg + static_cast<size_t>(blockIdx.x) * DBG_SLOTS;
+                d[DBG_MMA_WAIT_TEMPTY] = w_tempty.acc;
+                d[DBG_MMA_WAIT_FULL] = w_full.acc;
+            }
+        }
+        __syncwarp();
+    } else if (warp < WARP_UPD0) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
+        // ------------------------------------------------------------------ candidates: one frame per thread
+        // Scores are looked at eight at a time. Chunk 0 is read twice: first only for its minimum (branch-free), so
+        // that the filter pass starts with a threshold that is already within a few records of the final one; every
+        // later element then costs one FFMA and half a min, and the rare eight-group whose minimum is inside the
+        // window appends {group minimum, group id, 8-bit mask of its elements inside the window} to the frame's list.
+        const int q = warp & 3;                       // TMEM lane quarter this warp may touch
+        const int tid = q * 32 + lane;                // frame within the tile
+        const uint32_t ls = smem_u32(list_s) + tid * 4;      // entry e at + e * 512
+        const uint32_t li = smem_u32(list_i) + tid * 4;
+        // ||c||^2 of a chunk is staged in shared memory one chunk ahead by these four warps themselves (two floats
+        // per thread), so that scoring never waits on a global load.
+        const uint32_t cnbuf = smem_u32(smem + OFF_CN);
+        sts_f32x2(cnbuf + tid * 8, __ldg(reinterpret_cast<const float2*>(p.cn32) + tid));
+        uint32_t it = 0, job = 0;
+        WaitClock w_tfull(p.dbg != nullptr), w_cempty(p.dbg != nullptr), w_ld(p.dbg != nullptr);
+        unsigned long long n_events = 0;
+        const long long t_epi = w_tfull.begin();
+        for (int g0 = 0; g0 < my_tiles; g0 += group) {
+            const int gs = min(group, my_tiles - g0);
+            for (int l = 0; l < p.L; ++l) {
+                for (int i = g0; i < g0 + gs; ++i, ++job) {
+                    const int tile = blockIdx.x + i * gridDim.x;
+                    const long long row = static_cast<long long>(tile) * BLOCK_M + tid;
+                    const bool valid = row < p.n_rows;
+                    const float inf = __int_as_float(0x7F800000);
+                    float alpha = 0.f, window = 0.f;
+                    float m = inf;
+                    float thr = valid ? inf : -inf;   // frames outside the input never collect anything
+                    int cnt = 0;
+                    bool overflow = false;
+
+                    // drop list entries whose group minimum has fallen out of the (only ever shrinking) window
+                    auto compact = [&]() {
+                        int w = 0;
+                        for (int e = 0; e < cnt; ++e) {
+                            const float sv = lds_f32(ls + e * (BLOCK_M * 4));
+                            const uint32_t iv = lds_u32(li + e * (BLOCK_M * 4));
+                            if (sv <= thr) {
+                                sts_f32(ls + w * (BLOCK_M * 4), sv);
+                                sts_u32(li + w * (BLOCK_M * 4), iv);
+                                ++w;
+                            }
+                        }
+                        cnt = w;
+                    };
+
+                    for (int chunk = 0; chunk < n_chunks; ++chunk, ++it) {
+                        const uint32_t as = it & 1, aph = (it >> 1) & 1;
+                        const long long t0 = w_tfull.begin();
+                        mbar_wait(&tfull[as], aph);
+                        w_tfull.end(t0);
+                        tcgen05_fence_after();
+                        if (chunk == 0 && valid) {
+                            // written by this CTA's update warps one layer ago: only now is it known to be there
+                            const float4 ri = __ldcg(p.rowinfo + row);
+                            alpha = ri.x;
+                            window = ri.z;
+                        }
+                        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N;
+                        // (layer, chunk) after this one in the job sequence; past the end it wraps to (0, 0)
+                        int nl = l, nchunk = chunk + 1;
+                        if (nchunk == n_chunks) {
+                            nchunk = 0;
+                            if (i + 1 >= g0 + gs) nl = (l + 1 < p.L) ? l + 1 : 0;
+                        }
+                        const float2 cn_next = __ldg(reinterpret_cast<const float2*>(
+                                                         p.cn32 + static_cast<long long>(nl) * p.kp + nchunk * BLOCK_N) + tid);
+                        bar_sync_named(1, EPI_WARPS * 32);         // this chunk's buffer is complete and visible
+                        const uint32_t cn_s = cnbuf + (it & 1) * (BLOCK_N * 4);
+                        const int gid0 = (chunk * BLOCK_N) >> 3;
+
+                        // FILTER = false: running minimum only.  FILTER = true: minimum + list of groups in the window.
+                        auto scan32 = [&](const uint32_t (&v)[32], int g, bool filter) {
+                            float4 cq[8];
+#pragma unroll
+                            for (int h = 0; h < 8; ++h) cq[h] = lds_f32x4(cn_s + (g * 32 + h * 4) * 4);
+#pragma unroll
+                            for (int h = 0; h < 4; ++h) {
+                                const float4 c0 = cq[h * 2], c1 = cq[h * 2 + 1];
+                                float s[8];
+                                s[0] = fmaf(__uint_as_float(v[h * 8 + 0]), alpha, c0.x);
+                                s[1] = fmaf(__uint_as_float(v[h * 8 + 1]), alpha, c0.y);
+                                s[2] = fmaf(__uint_as_float(v[h * 8 + 2]), alpha, c0.z);
+                                s[3] = fmaf(__uint_as_float(v[h * 8 + 3]), alpha, c0.w);
+                                s[4] = fmaf(__uint_as_float(v[h * 8 + 4]), alpha, c1.x);
+                                s[5] = fmaf(__uint_as_float(v[h * 8 + 5]), alpha, c1.y);
+                                s[6] = fmaf(__uint_as_float(v[h * 8 + 6]), alpha, c1.z);
+                                s[7] = fmaf(__uint_as_float(v[h * 8 + 7]), alpha, c1.w);
+                                const float mn = fminf(fminf(fminf(fminf(s[0], s[1]), s[2]), fminf(fminf(s[3], s[4]), s[5])),
+                                                       fminf(fminf(s[6], s[7]), inf));
+                                if (!filter) {
+                                    m = fminf(m, mn);
+                                } else if (mn <= thr) {
+                                    ++n_events;
+                                    m = fminf(m, mn);
+                                    // m + W rounded up: the kept set must be a superset of the exact window
+                                    thr = fmaf(fabsf(m) + window, 2.4e-7f, m + window);
+                                    uint32_t mask = 0;
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) mask |= (s[e] <= thr) ? (1u << e) : 0u;
+                                    if (cnt == LCAP) compact();
+                                    if (cnt < LCAP) {
+                                        sts_f32(ls + cnt * (BLOCK_M * 4), mn);
+                                        sts_u32(li + cnt * (BLOCK_M * 4),
+                                                (static_cast<uint32_t>(gid0 + g * 4 + h) << 8) | mask);
+                                        ++cnt;
+                                    } else {
+                                        overflow = true;
+                                    }
+                                }
+                            }
+                        };
+
+                        uint32_t va[32];
+                        if (chunk == 0) {
+#pragma unroll 1
+                            for (int g = 0; g < BLOCK_N / 32; ++g) {
+                                tmem_ld_32x32b_x32(taddr + g * 32, va);
+                                { const long long tw = w_ld.begin(); tmem_wait_ld(); w_ld.end(tw); }
+                                if (p.dbg_mode < 6) scan32(va, g, false);
+                            }
+                            if (valid) thr = fmaf(fabsf(m) + window, 2.4e-7f, m + window);
+                        }
+#pragma unroll 1
+                        for (int g = 0; g < BLOCK_N / 32; ++g) {
+                            tmem_ld_32x32b_x32(taddr + g * 32, va);
+                            { const long long tw = w_ld.begin(); tmem_wait_ld(); w_ld.end(tw); }
+                            if (p.dbg_mode < 6) scan32(va, g, true);
+                        }
+                        // accumulator stage drained: hand it back to the MMA warp
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty[as]);
+                        sts_f32x2(cnbuf + ((it + 1) & 1) * (BLOCK_N * 4) + tid * 8, cn_next);
+                    }
+                    // hand the survivors to the update warps: u16 count + up to HCAP u16 code indices per frame
+                    compact();
+                    const uint32_t slot = job & 1;
+                    const long long t1 = w_cempty.begin();
+                    mbar_wait(&cempty[slot], ((job >> 1) & 1) ^ 1);
+                    w_cempty.end(t1);
+                    const uint32_t hrec = smem_u32(hand) + (slot * BLOCK_M + tid) * 16;
+                    unsigned n = 0;
+                    for (int e = 0; e < cnt; ++e) {
+                        const uint32_t iv = lds_u32(li + e * (BLOCK_M * 4));
+                        const uint32_t base = (iv >> 8) << 3;
+                        uint32_t mask = iv & 0xFFu;
+                        while (mask != 0) {
+                            const uint32_t b = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            if (n < HCAP) sts_u16(hrec + 2 + n * 2, static_cast<unsigned short>(base + b));
+                            ++n;
+                        }
+                    }
+                    if (p.dbg_mode >= 6) { n = 1; sts_u16(hrec + 2, 0); overflow = false; }
+                    if (!valid) n = 0;
+                    else if (overflow || n == 0 || n > HCAP) n = HAND_SCAN;
+                    sts_u16(hrec, static_cast<unsigned short>(n));
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&cfull[slot]);
+                }
+            }
+        }
+        if (p.dbg != nullptr && warp == WARP_EPI0 && lane == 0) {
+            unsigned long long* d = p.dbg + static_cast<size_t>(blockIdx.x) * DBG_SLOTS;
+            d[DBG_EPI_WAIT_TFULL] = w_tfull.acc;
+            d[DBG_EPI_WAIT_CEMPTY] = w_cempty.acc;
+            d[DBG_EPI_TOTAL] = clock64() - t_epi;
+            d[DBG_EPI_WAIT_LD] = w_ld.acc;
+            d[DBG_EPI_EVENTS] = n_events;
+        }
+    } else if (warp < WARP_TMA) {
+        if (REGS_UPD > 80) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_UPD));
+        // ------------------------------------------------------------------ update: one warp per frame
+        // Phase 0 settles the frames the coarse pass could not certify (exact fp64 re-rank, or the exact scan).
+        // Phase 1 is branch-free: row rr+1's residual and code vector are in flight while row rr is updated, and the
+        // warp reductions + error window of row rr-1 are scheduled under row rr's arithmetic. The operand scale of
+        // the next layer comes from a bound (max|r| + max|c|), not from the new row, so no element waits on a
+        // reduction; the exact new max is reduced afterwards and kept for the next layer's bound.
+        const int uw = warp - WARP_UPD0;
+        const int dp4 = p.dp >> 2;
+        uint32_t job = 0;
+        WaitClock w_cfull(p.dbg != nullptr), w_res(p.dbg != nullptr);
+        const long long t_upd = w_cfull.begin();
+        for (int g0 = 0; g0 < my_tiles; g0 += group) {
+            const int gs = min(group, my_tiles - g0);
+            for (int l = 0; l < p.L; ++l) {
+                const float* cb_l = p.cbf + static_cast<long long>(l) * p.K * p.dp;
+                const double* cn64_l = p.cn64 + static_cast<long long>(l) * p.K;
+                const bool last = l + 1 == p.L;
+                const rows::LayerConst* lc_next = last ? nullptr : p.lc + l + 1;
+                const float cabs = __ldg(&p.lc[l].cabs);
+                double* loss_l = p.row_loss != nullptr ? p.row_loss + static_cast<long long>(l) * p.loss_ld : nullptr;
+                const bool residual_needed = !last || loss_l != nullptr;
+                char* codes_l = static_cast<char*>(p.codes);
+                const long long code_base = static_cast<long long>(l) * p.codes_ld + p.code_off;
+                for (int i = g0; i < g0 + gs; ++i, ++job) {
+                    const int tile = blockIdx.x + i * gridDim.x;
+                    const int row0 = tile * BLOCK_M + uw * ROWS_PER_UPD_WARP;
+                    const int nrows = max(0, min(ROWS_PER_UPD_WARP, p.n_rows - row0));
+                    float am_old = 0.f;                // lane rr: max |r| of row rr before this layer
+                    if (residual_needed && nrows > 0) {
+                        // pull this warp's residual rows towards L2 while the tile's GEMM is still running
+                        const char* base = reinterpret_cast<const char*>(p.r + static_cast<long long>(row0) * p.dp);
+                        const int bytes = nrows * p.dp * 4;
+                        for (int off = lane * 128; off < bytes; off += 32 * 128) prefetch_l2(base + off);
+                        if (lane < nrows) am_old = __ldcg(p.rowamax + row0 + lane);
+                    }
+                    const uint32_t slot = job & 1;
+                    const long long t0 = w_cfull.begin();
+                    mbar_wait(&cfull[slot], (job >> 1) & 1);
+                    w_cfull.end(t0);
+                    uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+                    if (lane < ROWS_PER_UPD_WARP) rec = hand[slot * BLOCK_M + uw * ROWS_PER_UPD_WARP + lane];
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&cempty[slot]);
+                    if (p.dbg_mode == 3 || p.dbg_mode == 7) {
+                        __syncwarp();
+                        if (lane == 0) st_release(&ready[uw], job + 1);
+                        continue;
+                    }
+
+                    // ---- phase 0: decisions. lane rr ends up holding the code of row rr in jsel.
+                    const unsigned n_mine = rec.x & 0xFFFFu;
+                    int jsel = static_cast<int>(rec.x >> 16);
+                    unsigned todo = __ballot_sync(0xffffffffu, lane < nrows && n_mine != 1u);
+                    unsigned n_rerank = 0, n_scan = 0;
+                    const unsigned n_cert = static_cast<unsigned>(nrows) - __popc(todo);
+                    while (todo != 0) {
+                        const int rr = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const uint32_t h0 = __shfl_sync(0xffffffffu, rec.x, rr), h1 = __shfl_sync(0xffffffffu, rec.y, rr),
+                                       h2 = __shfl_sync(0xffffffffu, rec.z, rr), h3 = __shfl_sync(0xffffffffu, rec.w, rr);
+                        const unsigned n = h0 & 0xFFFFu;
+                        const unsigned cidx[HCAP] = {h0 >> 16, h1 & 0xFFFFu, h1 >> 16, h2 & 0xFFFFu,
+                                                     h2 >> 16, h3 & 0xFFFFu, h3 >> 16};
+                        float4 rv[NV];
+                        load_row<NV>(rv, reinterpret_cast<const float4*>(p.r + static_cast<long long>(row0 + rr) * p.dp), dp4, lane);
+                        double best = 0.0;
+                        int bestj = -1;
+                        if (n == HAND_SCAN) {
+                            // exact scan of every code, two in flight; k ascending so the first minimum is kept
+                            for (int k0 = 0; k0 < p.K; k0 += 2) {
+                                const int k1 = min(k0 + 1, p.K - 1);
+                                const double s0 = score_regs<NV>(rv, reinterpret_cast<const float4*>(cb_l + static_cast<long long>(k0) * p.dp),
+                                                                 dp4, cn64_l[k0], lane);
+                                const double s1 = score_regs<NV>(rv, reinterpret_cast<const float4*>(cb_l + static_cast<long long>(k1) * p.dp),
+                                                                 dp4, cn64_l[k1], lane);
+                                if (bestj < 0 || s0 < best) { best = s0; bestj = k0; }
+                                if (k1 > k0 && s1 < best) { best = s1; bestj = k1; }
+                            }
+                            ++n_scan;
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < HCAP; ++c) {
+                                if (c < static_cast<int>(n)) {                      // warp-uniform
+                                    const int k = min(static_cast<int>(cidx[c]), p.K - 1);
+                                    const double s = score_regs<NV>(rv, reinterpret_cast<const float4*>(cb_l + static_cast<long long>(k) * p.dp),
+                                                                    dp4, cn64_l[k], lane);
+                                    if (bestj < 0 || s < best || (s == best && k < bestj)) { best = s; bestj = k; }
+                                }
+                            }
+                            ++n_rerank;
+                        }
+                        if (lane == rr) jsel = bestj;
+                    }
+                    jsel = max(0, min(jsel, p.K - 1));
+                    if (lane < nrows) rows::store_code(codes_l, p.code_dtype, code_base + row0 + lane, jsel);
+
+                    // ---- phase 1: residual update, next operand, error window
+                    const long long tB = w_res.begin();
+                    if (!last && loss_l == nullptr && dp4 == NV * 32 && nrows > 0) {
+                        // Hot form: every lane holds exactly NV float4 of a row, nothing is predicated. One row at a
+                        // time per warp; the sixteen update warps of the CTA cover each other's memory latency.
+#pragma unroll 1
+                        for (int rr = 0; rr < nrows; ++rr) {
+                            const int row = row0 + rr;
+                            const int j = __shfl_sync(0xffffffffu, jsel, rr);
+                            float4* r4 = reinterpret_cast<float4*>(p.r + static_cast<long long>(row) * p.dp);
+                            const float4* c4 = reinterpret_cast<const float4*>(cb_l + static_cast<long long>(j) * p.dp);
+                            float4 cur[NV], cv[NV];
+#pragma unroll
+                            for (int k = 0; k < NV; ++k) cur[k] = __ldcg(r4 + k * 32 + lane);
+#pragma unroll
+                            for (int k = 0; k < NV; ++k) cv[k] = __ldcg(c4 + k * 32 + lane);
+                            // operand scale from the bound  max|r'| <= max|r| + max|c|
+                            const float bound = (__shfl_sync(0xffffffffu, am_old, rr) + cabs) * 1.00001f;
+                            const float sx = rows::pow2_scale_for(bound);
+                            const float2 sx2 = make_float2(sx, sx);
+                            uint2* a_row = reinterpret_cast<uint2*>(p.a + static_cast<long long>(row) * p.dp);
+                            float2 lo2v = make_float2(0.f, 0.f), xh2v = make_float2(0.f, 0.f);
+                            float amax = 0.f;
+#pragma unroll
+                            for (int k = 0; k < NV; ++k) {
+                                // q = codebook[j]; t = q - r; q_ste = r + t; r' = r - q_ste   (nat.py:2159, 2167, 1405)
+                                const float2 x01 = make_float2(cur[k].x, cur[k].y), x23 = make_float2(cur[k].z, cur[k].w);
+                                const float2 c01 = make_float2(cv[k].x, cv[k].y), c23 = make_float2(cv[k].z, cv[k].w);
+                                const float2 t01 = sub2(c01, x01), t23 = sub2(c23, x23);
+                                const float2 n01 = sub2(x01, __fadd2_rn(x01, t01)), n23 = sub2(x23, __fadd2_rn(x23, t23));
+                                r4[k * 32 + lane] = make_float4(n01.x, n01.y, n23.x, n23.y);
+                                amax = fmaxf(fmaxf(amax, fabsf(n01.x)), fmaxf(fabsf(n01.y), fmaxf(fabsf(n23.x), fabsf(n23.y))));
+                                const float2 s01 = __fmul2_rn(n01, sx2), s23 = __fmul2_rn(n23, sx2);
+                                const __half2 h01 = __float22half2_rn(s01), h23 = __float22half2_rn(s23);
+                                const float2 l01 = sub2(s01, __half22float2(h01)), l23 = sub2(s23, __half22float2(h23));
+                                lo2v = __ffma2_rn(l01, l01, lo2v);
+                                lo2v = __ffma2_rn(l23, l23, lo2v);
+                                xh2v = __ffma2_rn(s01, s01, xh2v);
+                                xh2v = __ffma2_rn(s23, s23, xh2v);
+                                uint2 packed;
+                                packed.x = *reinterpret_cast<const uint32_t*>(&h01);
+                                packed.y = *reinterpret_cast<const uint32_t*>(&h23);
+                                a_row[k * 32 + lane] = packed;
+                            }
+                            const float lo2 = warp_sum(lo2v.x + lo2v.y), xh2 = warp_sum(xh2v.x + xh2v.y), amx = warp_max(amax);
+                            if (lane == 0) {
+                                p.rowinfo[row] = rows::make_rowinfo_bound(sx, lo2, xh2, lc_next, p.dp);
+                                p.rowamax[row] = amx;
+                            }
+                        }
+                    } else
+                    if (residual_needed && nrows > 0) {
+                        // General form (ragged D, last layer with loss): same arithmetic, predicated per float4.
+#pragma unroll 1
+                        for (int rr = 0; rr < nrows; ++rr) {
+                            const int row = row0 + rr;
+                            const int j = __shfl_sync(0xffffffffu, jsel, rr);
+                            float4* r4 = reinterpret_cast<float4*>(p.r + static_cast<long long>(row) * p.dp);
+                            float4 cur[NV], cv[NV];
+                            load_row<NV>(cur, r4, dp4, lane);
+                            load_code<NV>(cv, reinterpret_cast<const float4*>(cb_l + static_cast<long long>(j) * p.dp), dp4, lane);
+                            const float bound = (__shfl_sync(0xffffffffu, am_old, rr) + cabs) * 1.00001f;
+                            const float sx = rows::pow2_scale_for(bound);
+                            const float2 sx2 = make_float2(sx, sx);
+                            uint2* a_row = reinterpret_cast<uint2*>(p.a + static_cast<long long>(row) * p.dp);
+                            float2 lo2v = make_float2(0.f, 0.f), xh2v = make_float2(0.f, 0.f);
+                            float amax = 0.f;
+                            double loss = 0.0;
+#pragma unroll
+                            for (int k = 0; k < NV; ++k) {
+                                const int qq = k * 32 + lane;
+                                if (qq < dp4) {
+                                    const float2 x01 = make_float2(cur[k].x, cur[k].y), x23 = make_float2(cur[k].z, cur[k].w);
+                                    const float2 c01 = make_float2(cv[k].x, cv[k].y), c23 = make_float2(cv[k].z, cv[k].w);
+                                    const float2 t01 = sub2(c01, x01), t23 = sub2(c23, x23);
+                                    const float2 n01 = sub2(x01, __fadd2_rn(x01, t01)), n23 = sub2(x23, __fadd2_rn(x23, t23));
+                                    if (loss_l != nullptr) {
+                                        loss += static_cast<double>(__fmul_rn(t01.x, t01.x));
+                                        loss += static_cast<double>(__fmul_rn(t01.y, t01.y));
+                                        loss += static_cast<double>(__fmul_rn(t23.x, t23.x));
+                                        loss += static_cast<double>(__fmul_rn(t23.y, t23.y));
+                                    }
+                                    if (!last) {
+                                        r4[qq] = make_float4(n01.x, n01.y, n23.x, n23.y);
+                                        amax = fmaxf(fmaxf(amax, fabsf(n01.x)), fmaxf(fabsf(n01.y), fmaxf(fabsf(n23.x), fabsf(n23.y))));
+                                        const float2 s01 = __fmul2_rn(n01, sx2), s23 = __fmul2_rn(n23, sx2);
+                                        const __half2 h01 = __float22half2_rn(s01), h23 = __float22half2_rn(s23);
+                                        const float2 l01 = sub2(s01, __half22float2(h01)), l23 = sub2(s23, __half22float2(h23));
+                                        lo2v = __ffma2_rn(l01, l01, lo2v);
+                                        lo2v = __ffma2_rn(l23, l23, lo2v);
+                                        xh2v = __ffma2_rn(s01, s01, xh2v);
+                                        xh2v = __ffma2_rn(s23, s23, xh2v);
+                                        uint2 packed;
+                                        packed.x = *reinterpret_cast<const uint32_t*>(&h01);
+                                        packed.y = *reinterpret_cast<const uint32_t*>(&h23);
+                                        a_row[qq] = packed;
+                                    }
+                                }
+                            }
+                            if (loss_l != nullptr) {
+                                loss = warp_sum(loss);
+                                if (lane == 0) loss_l[row] = loss;
+                            }
+                            if (!last) {
+                                const float lo2 = warp_sum(lo2v.x + lo2v.y), xh2 = warp_sum(xh2v.x + xh2v.y), amx = warp_max(amax);
+                                if (lane == 0) {
+                                    p.rowinfo[row] = rows::make_rowinfo_bound(sx, lo2, xh2, lc_next, p.dp);
+                                    p.rowamax[row] = amx;
+                                }
+                            }
+                        }
+                    }
+                    w_res.end(tB);
+                    // publish this warp's share of the job: global writes -> visible to the TMA (async proxy)
+                    __threadfence();
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        st_release(&ready[uw], job + 1);
+                        if (p.stats != nullptr) {
+                            unsigned long long* st = p.stats + l * 4;
+                            if (n_cert) atomicAdd(st + 0, static_cast<unsigned long long>(n_cert));
+                            if (n_rerank) atomicAdd(st + 1, static_cast<unsigned long long>(n_rerank));
+                            if (n_scan) atomicAdd(st + 2, static_cast<unsigned long long>(n_scan));
+                        }
+                    }
+                }
+            }
+        }
+        if (p.dbg != nullptr && uw == 0 && lane == 0) {
+            unsigned long long* d = p.dbg + static_cast<size_t>(blockIdx.x) * DBG_SLOTS;
+            d[DBG_UPD_WAIT_CFULL] = w_cfull.acc;
+            d[DBG_UPD_TOTAL] = clock64() - t_upd;
+            d[DBG_UPD_RESID] = w_res.acc;
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == WARP_MMA) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+}  // namespace stack
+}  // namespace nat

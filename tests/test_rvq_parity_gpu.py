@@ -291,3 +291,52 @@ def test_two_lane_overlap_matches_single_stream():
                      outs[0][0][:, :4000].reshape(L, 1, 4000).cpu().numpy())
     finally:
         lib.nat_rvq_codebooks_destroy(handle)
+
+
+@pytest.mark.parametrize("D,K,L,N", [(256, 512, 4, 60_000), (768, 1024, 4, 40_000), (1024, 1024, 2, 20_000),
+                                      (96, 300, 3, 1000)])
+def test_fused_stack_kernel_equals_layer_kernels(D, K, L, N, monkeypatch):
+    """The one-launch stack kernel (any tile grouping) and the per-layer kernels take the same exact decisions:
+    indices, quantised sum, per-layer losses and decision counters are identical."""
+    from neural_audio_tokenizer_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(D * 7 + K)
+    cbs = [torch.randn(K, D, device="cuda") for _ in range(L)]
+    x = torch.randn(1, D, N, device="cuda")
+    ptrs = (ctypes.c_void_p * L)(*[c.data_ptr() for c in cbs])
+    handle = ctypes.c_void_p()
+    _lib.check(lib.nat_rvq_codebooks_create(ptrs, L, K, D, None, ctypes.byref(handle)))
+    try:
+        ws_bytes = lib.nat_rvq_workspace_bytes(handle, N)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+
+        def run(fused, group, want_q_loss):
+            monkeypatch.setenv("NAT_RVQ_FUSED", "1" if fused else "0")
+            monkeypatch.setenv("NAT_RVQ_GROUP", str(group))
+            codes = torch.full((L, N), -1, dtype=torch.int32, device="cuda")
+            q = torch.empty_like(x) if want_q_loss else None
+            loss = torch.empty(L, device="cuda") if want_q_loss else None
+            stats = torch.zeros((L, 4), dtype=torch.int64, device="cuda")
+            _lib.check(lib.nat_rvq_encode_f32(handle, x.data_ptr(), _lib.LAYOUT_BCT, 1, N, codes.data_ptr(),
+                                              _lib.CODES_I32, q.data_ptr() if q is not None else None,
+                                              loss.data_ptr() if loss is not None else None, 0.25, stats.data_ptr(),
+                                              ws.data_ptr(), ws_bytes, 0, torch.cuda.current_stream().cuda_stream))
+            torch.cuda.synchronize()
+            return codes, q, loss, stats
+
+        base = run(False, 2, True)
+        assert (base[3][:, :3].sum(dim=1) == N).all()
+        for group in (1, 2, 3, 1 << 20):
+            for want in (True, False):
+                got = run(True, group, want)
+                assert torch.equal(got[0], base[0]), f"group {group}: indices differ from the per-layer kernels"
+                assert (got[3][:, :3].sum(dim=1) == N).all(), got[3]
+                if want:
+                    assert torch.equal(got[1], base[1])
+                    assert torch.equal(got[2], base[2])
+        if N <= 20_000:
+            ref = rvq_oracle.rvq_encode(x.cpu(), [c.cpu() for c in cbs])
+            _check_codes(x.cpu(), torch.stack([c.cpu() for c in cbs]), np.stack([r.numpy() for r in ref]),
+                         base[0].view(L, 1, N).cpu().numpy())
+    finally:
+        lib.nat_rvq_codebooks_destroy(handle)
