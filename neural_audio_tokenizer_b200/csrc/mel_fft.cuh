@@ -1,4 +1,4 @@
-// Front-end kernels: framed 2048-point real DFT in shared memory with fused epilogues.
+// Front-end kernels: framed 2048-point real DFT with fused epilogues.
 //
 //   MEL mode       replaces torchaudio MelSpectrogram(n_fft=2048, hop, n_mels, normalized=True) as the reference
 //                  builds it at nat.py:2281-2290: reflect padding, periodic Hann, /sum(w^2), |.|^2, banded
@@ -6,9 +6,11 @@
 //   SPECTRAL mode  replaces the per-frame rfft loop of nat.py:2405-2430: |X| + 1e-12, centroid and bandwidth.
 //
 // Two real frames share one complex FFT (frame a in the real lane, frame b in the imaginary lane) and are separated
-// afterwards with the conjugate-symmetry identities. The transform is an in-place radix-2 decimation-in-frequency
-// pass over a 16 KB shared buffer (natural order in, bit-reversed out; the epilogue reads through __brev).
-// A CTA owns 8 consecutive frames so that the [n_mels, T] output is written in 32-byte runs.
+// afterwards with the conjugate-symmetry identities. The transform is a three-pass decimation-in-frequency
+// 2048 = 16 x 16 x 8 by a team of 128 threads with 16 points per thread in registers: pass 1 reads the windowed
+// samples straight from global memory, passes 2 and 3 exchange through a padded, bank-conflict-free 19 KB shared
+// buffer; the spectrum is left in digit-reversed order and the epilogue indexes it through fft_pos().
+// A CTA is two teams and owns 8 consecutive frames so that the [n_mels, T] output is written in 32-byte runs.
 #pragma once
 
 #include "nat_common.cuh"
@@ -17,33 +19,101 @@ namespace nat {
 namespace fe {
 
 constexpr int NFFT = 2048;
-constexpr int LOG2N = 11;
 constexpr int NBINS = NFFT / 2 + 1;
-constexpr int THREADS = 256;
+constexpr int TEAM = 128;                    // threads per FFT
+constexpr int THREADS = 256;                 // two teams per CTA
 constexpr int FRAMES_PER_CTA = 8;
 constexpr int MAX_MELS = 256;
+constexpr int FFT_BUF = NFFT + NFFT / 8 + 8 * (NFFT / 128);      // padded complex elements per transform
 
-// One butterfly sweep of the DIF transform, callable from host code too (tests replay it on the CPU).
-__host__ __device__ inline void dif_stage(float2* x, const float2* tw, int half, int tid, int nthreads) {
-    const int tw_stride = (NFFT / 2) / half;
-    for (int j = tid; j < NFFT / 2; j += nthreads) {
-        const int pos = j & (half - 1);
-        const int i0 = ((j - pos) << 1) + pos;
-        const int i1 = i0 + half;
-        const float2 u = x[i0], v = x[i1];
-        const float2 w = tw[pos * tw_stride];
-        const float dx = u.x - v.x, dy = u.y - v.y;
-        x[i0] = make_float2(u.x + v.x, u.y + v.y);
-        x[i1] = make_float2(dx * w.x - dy * w.y, dx * w.y + dy * w.x);
-    }
+// ---- small in-register DFTs (forward, e^{-2 pi i / n}), natural order in and out
+__host__ __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__host__ __device__ __forceinline__ float2 cmul(float2 a, float2 w) {
+    return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
+}
+__host__ __device__ __forceinline__ void fft4(float2& a0, float2& a1, float2& a2, float2& a3) {
+    const float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = csub(a1, a3);
+    a0 = cadd(t0, t2);
+    a2 = csub(t0, t2);
+    a1 = make_float2(t1.x + t3.y, t1.y - t3.x);      // t1 - i t3
+    a3 = make_float2(t1.x - t3.y, t1.y + t3.x);      // t1 + i t3
+}
+__host__ __device__ __forceinline__ void fft8(float2 (&a)[8]) {
+    float2 e0 = a[0], e1 = a[2], e2 = a[4], e3 = a[6], o0 = a[1], o1 = a[3], o2 = a[5], o3 = a[7];
+    fft4(e0, e1, e2, e3);
+    fft4(o0, o1, o2, o3);
+    const float h = 0.70710678118654752440f;
+    o1 = make_float2((o1.x + o1.y) * h, (o1.y - o1.x) * h);      // * e^{-i pi/4}
+    o2 = make_float2(o2.y, -o2.x);                               // * -i
+    o3 = make_float2((o3.y - o3.x) * h, -(o3.x + o3.y) * h);     // * e^{-3 i pi/4}
+    a[0] = cadd(e0, o0); a[4] = csub(e0, o0);
+    a[1] = cadd(e1, o1); a[5] = csub(e1, o1);
+    a[2] = cadd(e2, o2); a[6] = csub(e2, o2);
+    a[3] = cadd(e3, o3); a[7] = csub(e3, o3);
+}
+__host__ __device__ __forceinline__ void fft16(float2 (&a)[16]) {
+    float2 e[8], o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { e[i] = a[2 * i]; o[i] = a[2 * i + 1]; }
+    fft8(e);
+    fft8(o);
+    // e^{-2 pi i k / 16}, k = 1..7
+    const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f, h = 0.70710678118654752440f;
+    o[1] = cmul(o[1], make_float2(c1, -s1));
+    o[2] = cmul(o[2], make_float2(h, -h));
+    o[3] = cmul(o[3], make_float2(s1, -c1));
+    o[4] = make_float2(o[4].y, -o[4].x);
+    o[5] = cmul(o[5], make_float2(-s1, -c1));
+    o[6] = cmul(o[6], make_float2(-h, -h));
+    o[7] = cmul(o[7], make_float2(-c1, -s1));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a[k] = cadd(e[k], o[k]); a[k + 8] = csub(e[k], o[k]); }
 }
 
-__device__ __forceinline__ int brev11(int k) { return static_cast<int>(__brev(static_cast<unsigned>(k)) >> (32 - LOG2N)); }
+// Physical slot of logical element i: one pad per 8 and eight more per 128 make all three passes conflict-free.
+__host__ __device__ __forceinline__ int fft_phys(int i) { return i + (i >> 3) + ((i >> 7) << 3); }
+// Where X[k] lands: k = k1 + 16 k2 + 256 k3  ->  logical k1 * 128 + k2 * 8 + k3.
+__host__ __device__ __forceinline__ int fft_pos(int k) { return fft_phys(((k & 15) << 7) + (((k >> 4) & 15) << 3) + (k >> 8)); }
+// e^{-2 pi i e / 2048} for 0 <= e < 2048 from the half table tw[k] = e^{-2 pi i k / 2048}, k < 1024.
+__host__ __device__ __forceinline__ float2 fft_tw(const float2* tw, int e) {
+    const float2 w = tw[e & (NFFT / 2 - 1)];
+    return (e & (NFFT / 2)) ? make_float2(-w.x, -w.y) : w;
+}
+
+// The three passes for thread t of a team; a barrier over the team separates them. `in` holds x[128 n + t], n < 16.
+__host__ __device__ __forceinline__ void fft_pass1(float2* S, const float2* tw, int t, float2 (&a)[16]) {
+    fft16(a);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) S[fft_phys(k * 128 + t)] = k == 0 ? a[0] : cmul(a[k], fft_tw(tw, t * k));
+}
+__host__ __device__ __forceinline__ void fft_pass2(float2* S, const float2* tw, int t) {
+    const int s = t >> 3, n2 = t & 7;
+    float2 a[16];
+#pragma unroll
+    for (int n = 0; n < 16; ++n) a[n] = S[fft_phys(s * 128 + 8 * n + n2)];
+    fft16(a);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) S[fft_phys(s * 128 + k * 8 + n2)] = k == 0 ? a[0] : cmul(a[k], fft_tw(tw, 16 * n2 * k));
+}
+__host__ __device__ __forceinline__ void fft_pass3(float2* S, int t) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int u = t + h * TEAM;
+        float2 a[8];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) a[n] = S[fft_phys(u * 8 + n)];
+        fft8(a);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) S[fft_phys(u * 8 + k)] = a[k];
+    }
+}
 
 __device__ __forceinline__ float hann_from_tw(const float2* tw, int n) {
     // periodic Hann: 0.5 - 0.5 cos(2 pi n / N); tw[k].x = cos(2 pi k / N) for k < N/2
     return n < NFFT / 2 ? 0.5f - 0.5f * tw[n].x : 0.5f + 0.5f * tw[n - NFFT / 2].x;
 }
+__device__ __forceinline__ void team_sync(int team) { asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(TEAM) : "memory"); }
 
 struct MelArgs {
     const float* wave;      // [B, S]
@@ -68,38 +138,48 @@ __device__ __forceinline__ float frame_sample(const float* __restrict__ w, long 
     return __ldg(w + j);
 }
 
-// Transform frames f and f+1 (f+1 may not exist) of one clip: smem x holds the bit-reversed spectrum of a + i b.
+// Transform frames a and b (b may not exist) of one clip by one team: S ends up holding the digit-reversed spectrum
+// of a + i b (read it through fft_pos). Ends with a team barrier.
 template <bool SPECTRAL>
-__device__ __forceinline__ void fft_frame_pair(float2* x, const float2* tw_s, const float* __restrict__ wave,
-                                               long long S, long long start_a, bool has_b, long long start_b) {
-    for (int n = threadIdx.x; n < NFFT; n += THREADS) {
-        const float wn = hann_from_tw(tw_s, n);
-        const float a = frame_sample<SPECTRAL>(wave, S, start_a + n) * wn;
-        const float b = has_b ? frame_sample<SPECTRAL>(wave, S, start_b + n) * wn : 0.f;
-        x[n] = make_float2(a, b);
+__device__ __forceinline__ void fft_frame_pair(float2* S, const float2* tw_s, const float* __restrict__ wave,
+                                               long long len, long long start_a, bool has_b, long long start_b,
+                                               int team, int t) {
+    float2 a[16];
+#pragma unroll
+    for (int n = 0; n < 16; ++n) {
+        const int idx = n * TEAM + t;
+        const float wn = hann_from_tw(tw_s, idx);
+        const float va = frame_sample<SPECTRAL>(wave, len, start_a + idx) * wn;
+        const float vb = has_b ? frame_sample<SPECTRAL>(wave, len, start_b + idx) * wn : 0.f;
+        a[n] = make_float2(va, vb);
     }
-    __syncthreads();
-#pragma unroll 1
-    for (int half = NFFT / 2; half >= 1; half >>= 1) {
-        dif_stage(x, tw_s, half, threadIdx.x, THREADS);
-        __syncthreads();
-    }
+    fft_pass1(S, tw_s, t, a);
+    team_sync(team);
+    fft_pass2(S, tw_s, t);
+    team_sync(team);
+    fft_pass3(S, t);
+    team_sync(team);
 }
 
 // X_a[k], X_b[k] from Z = FFT(a + i b):  X_a = (Z[k] + conj Z[N-k]) / 2,  X_b = (Z[k] - conj Z[N-k]) / (2i)
-__device__ __forceinline__ void split_bins(const float2* x, int k, float2& xa, float2& xb) {
-    const float2 z = x[brev11(k)];
-    const float2 y = x[brev11((NFFT - k) & (NFFT - 1))];
+__device__ __forceinline__ void split_bins(const float2* S, int k, float2& xa, float2& xb) {
+    const float2 z = S[fft_pos(k)];
+    const float2 y = S[fft_pos((NFFT - k) & (NFFT - 1))];
     xa = make_float2(0.5f * (z.x + y.x), 0.5f * (z.y - y.y));
     xb = make_float2(0.5f * (z.y + y.y), 0.5f * (y.x - z.x));
 }
 
 __global__ void __launch_bounds__(THREADS)
 mel_power_kernel(MelArgs p, long long groups_per_clip, long long total_groups) {
-    __shared__ float2 x[NFFT];
-    __shared__ float2 tw_s[NFFT / 2];
-    __shared__ float pw[2][NBINS + 3];
-    __shared__ float out_tile[MAX_MELS][FRAMES_PER_CTA + 1];
+    extern __shared__ __align__(16) unsigned char fe_smem[];
+    float2* tw_s = reinterpret_cast<float2*>(fe_smem);                               // [NFFT / 2]
+    float2* S_all = tw_s + NFFT / 2;                                                  // [2][FFT_BUF]
+    float* pw_all = reinterpret_cast<float*>(S_all + 2 * FFT_BUF);                    // [2][2][NBINS + 3]
+    float* out_tile = pw_all + 4 * (NBINS + 3);                                       // [n_mels][FRAMES_PER_CTA + 1]
+    const int team = threadIdx.x / TEAM, t = threadIdx.x % TEAM;
+    float2* S = S_all + team * FFT_BUF;
+    float* pw0 = pw_all + team * 2 * (NBINS + 3);
+    float* pw1 = pw0 + NBINS + 3;
     for (int i = threadIdx.x; i < NFFT / 2; i += THREADS) tw_s[i] = p.tw[i];
     __syncthreads();
     for (long long grp = blockIdx.x; grp < total_groups; grp += gridDim.x) {
@@ -107,37 +187,44 @@ mel_power_kernel(MelArgs p, long long groups_per_clip, long long total_groups) {
         const long long f0 = (grp - b * groups_per_clip) * FRAMES_PER_CTA;
         const float* wave = p.wave + b * p.S;
         const int nf = static_cast<int>(min(static_cast<long long>(FRAMES_PER_CTA), p.T - f0));
-        for (int pr = 0; pr < nf; pr += 2) {
+        // team 0 takes frames 0..3 of the group, team 1 frames 4..7, two frames per transform
+        for (int pr = team * 4; pr < team * 4 + 4; pr += 2) {
+            if (pr >= nf) break;                                                      // team-uniform
             const bool has_b = pr + 1 < nf;
-            fft_frame_pair<false>(x, tw_s, wave, p.S, (f0 + pr) * p.hop, has_b, (f0 + pr + 1) * p.hop);
-            for (int k = threadIdx.x; k < NBINS; k += THREADS) {
+            fft_frame_pair<false>(S, tw_s, wave, p.S, (f0 + pr) * p.hop, has_b, (f0 + pr + 1) * p.hop, team, t);
+            for (int k = t; k < NBINS; k += TEAM) {
                 float2 xa, xb;
-                split_bins(x, k, xa, xb);
-                pw[0][k] = (xa.x * xa.x + xa.y * xa.y) * p.inv_wsum;
-                pw[1][k] = (xb.x * xb.x + xb.y * xb.y) * p.inv_wsum;
+                split_bins(S, k, xa, xb);
+                pw0[k] = (xa.x * xa.x + xa.y * xa.y) * p.inv_wsum;
+                pw1[k] = (xb.x * xb.x + xb.y * xb.y) * p.inv_wsum;
             }
-            __syncthreads();
-            for (int o = threadIdx.x; o < 2 * p.n_mels; o += THREADS) {
+            team_sync(team);
+            for (int o = t; o < 2 * p.n_mels; o += TEAM) {
                 const int which = o / p.n_mels, m = o - which * p.n_mels;
                 const int2 be = __ldg(&p.band[m]);
                 const float* fb = p.fbT + static_cast<long long>(m) * NBINS;
+                const float* pw = which ? pw1 : pw0;
                 float acc = 0.f;
-                for (int k = be.x; k < be.y; ++k) acc = fmaf(pw[which][k], __ldg(fb + k), acc);
-                out_tile[m][pr + which] = acc;
+                for (int k = be.x; k < be.y; ++k) acc = fmaf(pw[k], __ldg(fb + k), acc);
+                out_tile[m * (FRAMES_PER_CTA + 1) + pr + which] = acc;
             }
-            __syncthreads();
+            team_sync(team);
         }
+        __syncthreads();
         for (int o = threadIdx.x; o < p.n_mels * FRAMES_PER_CTA; o += THREADS) {
             const int m = o / FRAMES_PER_CTA, fr = o - m * FRAMES_PER_CTA;
             if (fr < nf) {
                 const long long at = (b * p.n_mels + m) * p.T + f0 + fr;
-                const float v = out_tile[m][fr];
+                const float v = out_tile[m * (FRAMES_PER_CTA + 1) + fr];
                 p.mel[at] = v;
                 if (p.logmel != nullptr) p.logmel[at] = 10.f * log10f(fmaxf(v, 1e-10f));
             }
         }
         __syncthreads();
     }
+}
+constexpr size_t mel_smem_bytes(int n_mels) {
+    return sizeof(float2) * (NFFT / 2 + 2 * FFT_BUF) + sizeof(float) * (4 * (NBINS + 3) + n_mels * (FRAMES_PER_CTA + 1));
 }
 
 struct SpectralArgs {
@@ -150,60 +237,70 @@ struct SpectralArgs {
     float* out;             // [2, T]
 };
 
-__device__ __forceinline__ float block_sum_128(float v, float* sh, int tid128) {
-    // two independent 128-thread halves (one per frame of the pair) reduce side by side
+// Sum over the 128 threads of a team (one team per frame pair; each half-team... see caller). Ends with team barriers.
+__device__ __forceinline__ float team_sum(float v, float* sh, int team, int t) {
     v = warp_sum(v);
-    const int half = threadIdx.x >> 7, w = (threadIdx.x >> 5) & 3;
-    if ((threadIdx.x & 31) == 0) sh[half * 4 + w] = v;
-    __syncthreads();
-    const float r = sh[half * 4 + 0] + sh[half * 4 + 1] + sh[half * 4 + 2] + sh[half * 4 + 3];
-    __syncthreads();
-    (void)tid128;
+    if ((t & 31) == 0) sh[team * 4 + (t >> 5)] = v;
+    team_sync(team);
+    const float r = sh[team * 4 + 0] + sh[team * 4 + 1] + sh[team * 4 + 2] + sh[team * 4 + 3];
+    team_sync(team);
     return r;
 }
 
 __global__ void __launch_bounds__(THREADS)
 spectral_stats_kernel(SpectralArgs p) {
-    __shared__ float2 x[NFFT];
-    __shared__ float2 tw_s[NFFT / 2];
-    __shared__ float mag[2][NBINS + 3];
+    extern __shared__ __align__(16) unsigned char fe_smem[];
+    float2* tw_s = reinterpret_cast<float2*>(fe_smem);                               // [NFFT / 2]
+    float2* S_all = tw_s + NFFT / 2;                                                  // [2][FFT_BUF]
+    float* mag_all = reinterpret_cast<float*>(S_all + 2 * FFT_BUF);                   // [2][2][NBINS + 3]
     __shared__ float red[8];
+    const int team = threadIdx.x / TEAM, t = threadIdx.x % TEAM;
+    float2* S = S_all + team * FFT_BUF;
+    float* mag0 = mag_all + team * 2 * (NBINS + 3);
+    float* mag1 = mag0 + NBINS + 3;
     for (int i = threadIdx.x; i < NFFT / 2; i += THREADS) tw_s[i] = p.tw[i];
     __syncthreads();
     const long long pairs = (p.T + 1) / 2;
-    for (long long pr = blockIdx.x; pr < pairs; pr += gridDim.x) {
+    // one frame pair per team and iteration
+    for (long long pr = static_cast<long long>(blockIdx.x) * 2 + team; pr < pairs; pr += static_cast<long long>(gridDim.x) * 2) {
         const long long fa = 2 * pr, fb = fa + 1;
         const bool has_b = fb < p.T;
-        fft_frame_pair<true>(x, tw_s, p.wave, p.S, fa * p.hop, has_b, fb * p.hop);
-        for (int k = threadIdx.x; k < NBINS; k += THREADS) {
+        fft_frame_pair<true>(S, tw_s, p.wave, p.S, fa * p.hop, has_b, fb * p.hop, team, t);
+        for (int k = t; k < NBINS; k += TEAM) {
             float2 xa, xb;
-            split_bins(x, k, xa, xb);
-            mag[0][k] = sqrtf(xa.x * xa.x + xa.y * xa.y) + 1e-12f;          // nat.py:2418
-            mag[1][k] = sqrtf(xb.x * xb.x + xb.y * xb.y) + 1e-12f;
+            split_bins(S, k, xa, xb);
+            mag0[k] = sqrtf(xa.x * xa.x + xa.y * xa.y) + 1e-12f;          // nat.py:2418
+            mag1[k] = sqrtf(xb.x * xb.x + xb.y * xb.y) + 1e-12f;
         }
-        __syncthreads();
-        const int which = threadIdx.x >> 7, t = threadIdx.x & 127;
-        float sm = 0.f, smf = 0.f;
-        for (int k = t; k < NBINS; k += 128) {
-            const float m = mag[which][k];
-            sm += m;
-            smf = fmaf(m, static_cast<float>(k) * p.bin_hz, smf);
+        team_sync(team);
+        for (int which = 0; which < 2; ++which) {
+            if (which == 1 && !has_b) break;                               // team-uniform
+            const float* mag = which ? mag1 : mag0;
+            float sm = 0.f, smf = 0.f;
+            for (int k = t; k < NBINS; k += TEAM) {
+                const float m = mag[k];
+                sm += m;
+                smf = fmaf(m, static_cast<float>(k) * p.bin_hz, smf);
+            }
+            const float total = team_sum(sm, red, team, t) + 1e-8f;        // nat.py:2425
+            const float centroid = team_sum(smf, red, team, t) / total;    // nat.py:2426
+            float sv = 0.f;
+            for (int k = t; k < NBINS; k += TEAM) {
+                const float d = static_cast<float>(k) * p.bin_hz - centroid;
+                sv = fmaf(mag[k], d * d, sv);
+            }
+            const float var = team_sum(sv, red, team, t) / total;          // nat.py:2429-2430
+            if (t == 0) {
+                const long long f = which == 0 ? fa : fb;
+                p.out[f] = centroid;
+                p.out[p.T + f] = sqrtf(var);
+            }
         }
-        const float total = block_sum_128(sm, red, t) + 1e-8f;                // nat.py:2425
-        const float centroid = block_sum_128(smf, red, t) / total;            // nat.py:2426
-        float sv = 0.f;
-        for (int k = t; k < NBINS; k += 128) {
-            const float d = static_cast<float>(k) * p.bin_hz - centroid;
-            sv = fmaf(mag[which][k], d * d, sv);
-        }
-        const float var = block_sum_128(sv, red, t) / total;                  // nat.py:2429-2430
-        if (t == 0 && (which == 0 || has_b)) {
-            const long long f = which == 0 ? fa : fb;
-            p.out[f] = centroid;
-            p.out[p.T + f] = sqrtf(var);
-        }
-        __syncthreads();
+        team_sync(team);
     }
+}
+constexpr size_t spectral_smem_bytes() {
+    return sizeof(float2) * (NFFT / 2 + 2 * FFT_BUF) + sizeof(float) * 4 * (NBINS + 3);
 }
 
 // dense [NBINS, n_mels] filterbank -> band-major copy + per-band non-zero range (one CTA per band)

@@ -782,8 +782,14 @@ int nat_mel_power_f32(const float* wave_dev, int64_t B, int64_t S, int sample_ra
     }
     const long long groups_per_clip = (p.T + fe::FRAMES_PER_CTA - 1) / fe::FRAMES_PER_CTA;
     const long long total = groups_per_clip * B;
-    const int grid = static_cast<int>(std::min<long long>(total, plan->sm_count * 5LL * 4));
-    NAT_LAUNCH(7, st, fe::mel_power_kernel<<<grid, fe::THREADS, 0, st>>>(p, groups_per_clip, total));
+    const size_t smem = fe::mel_smem_bytes(n_mels);
+    static std::atomic<size_t> mel_smem_set{0};
+    if (mel_smem_set.load() < smem) {
+        NAT_CUDA(cudaFuncSetAttribute(fe::mel_power_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        mel_smem_set.store(smem);
+    }
+    const int grid = static_cast<int>(std::min<long long>(total, plan->sm_count * 4LL * 4));
+    NAT_LAUNCH(7, st, fe::mel_power_kernel<<<grid, fe::THREADS, smem, st>>>(p, groups_per_clip, total));
     NAT_CUDA(cudaGetLastError());
     return NAT_OK;
 }
@@ -800,8 +806,14 @@ int nat_spectral_stats_f32(const float* wave_dev, int64_t S, int sample_rate, in
     p.wave = wave_dev; p.S = S; p.T = nat_spectral_num_frames(S, n_fft, hop); p.hop = hop;
     p.bin_hz = static_cast<float>(sample_rate) / fe::NFFT; p.tw = plan->tw; p.out = out_dev;
     const long long pairs = (p.T + 1) / 2;
-    const int grid = static_cast<int>(std::min<long long>(pairs, plan->sm_count * 5LL * 4));
-    NAT_LAUNCH(7, static_cast<cudaStream_t>(stream), fe::spectral_stats_kernel<<<grid, fe::THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p));
+    const size_t smem = fe::spectral_smem_bytes();
+    static std::atomic<bool> spectral_smem_set{false};
+    if (!spectral_smem_set.load()) {
+        NAT_CUDA(cudaFuncSetAttribute(fe::spectral_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        spectral_smem_set.store(true);
+    }
+    const int grid = static_cast<int>(std::min<long long>((pairs + 1) / 2, plan->sm_count * 4LL * 4));
+    NAT_LAUNCH(7, static_cast<cudaStream_t>(stream), fe::spectral_stats_kernel<<<grid, fe::THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p));
     NAT_CUDA(cudaGetLastError());
     return NAT_OK;
 }

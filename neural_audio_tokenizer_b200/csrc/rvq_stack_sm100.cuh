@@ -498,7 +498,7 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
         const int uw = warp - WARP_UPD0;
         const int dp4 = p.dp >> 2;
         uint32_t job = 0;
-        WaitClock w_cfull(p.dbg != nullptr), w_res(p.dbg != nullptr);
+        WaitClock w_cfull(p.dbg != nullptr), w_res(p.dbg != nullptr), w_dec(p.dbg != nullptr), w_fence(p.dbg != nullptr);
         const long long t_upd = w_cfull.begin();
         for (int g0 = 0; g0 < my_tiles; g0 += group) {
             const int gs = min(group, my_tiles - g0);
@@ -539,6 +539,7 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
                     }
 
                     // ---- phase 0: decisions. lane rr ends up holding the code of row rr in jsel.
+                    const long long tA = w_dec.begin();
                     const unsigned n_mine = rec.x & 0xFFFFu;
                     int jsel = static_cast<int>(rec.x >> 16);
                     unsigned todo = __ballot_sync(0xffffffffu, lane < nrows && n_mine != 1u);
@@ -585,6 +586,7 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
                     jsel = max(0, min(jsel, p.K - 1));
                     if (lane < nrows) rows::store_code(codes_l, p.code_dtype, code_base + row0 + lane, jsel);
 
+                    w_dec.end(tA);
                     // ---- phase 1: residual update, next operand, error window
                     const long long tB = w_res.begin();
                     if (!last && loss_l == nullptr && dp4 == NV * 32 && nrows > 0) {
@@ -699,9 +701,11 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
                     }
                     w_res.end(tB);
                     // publish this warp's share of the job: global writes -> visible to the TMA (async proxy)
+                    const long long tD = w_fence.begin();
                     __threadfence();
                     fence_proxy_async();
                     __syncwarp();
+                    w_fence.end(tD);
                     if (lane == 0) {
                         st_release(&ready[uw], job + 1);
                         if (p.stats != nullptr) {
@@ -719,6 +723,8 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
             d[DBG_UPD_WAIT_CFULL] = w_cfull.acc;
             d[DBG_UPD_TOTAL] = clock64() - t_upd;
             d[DBG_UPD_RESID] = w_res.acc;
+            d[DBG_UPD_DECIDE] = w_dec.acc;
+            d[DBG_UPD_FENCE] = w_fence.acc;
         }
     }
 

@@ -13,9 +13,9 @@ h = rvq._pack.get(rvq._codebooks())
 wsb = lib.nat_rvq_workspace_bytes(h, N); ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
 st = torch.cuda.current_stream().cuda_stream
 base = None
-variants = [("0", "2")] + [("1", g) for g in os.environ.get("PROBE_GROUPS", "1,2,3,4,1000000").split(",")]
-for fused, group in variants:
-    os.environ["NAT_RVQ_FUSED"] = fused; os.environ["NAT_RVQ_GROUP"] = group
+variants = [("0", "2", "0")] + [("1", g, hh) for g in os.environ.get("PROBE_GROUPS", "1,2,3,4,1000000").split(",") for hh in os.environ.get("PROBE_HINTS", "0").split(",")]
+for fused, group, hints in variants:
+    os.environ["NAT_RVQ_FUSED"] = fused; os.environ["NAT_RVQ_GROUP"] = group; os.environ["NAT_RVQ_L2_HINTS"] = hints
     codes = torch.empty((4, N), dtype=torch.int16, device="cuda")
     prof = (ctypes.c_float * 8)()
     for rep in range(2):
@@ -32,7 +32,7 @@ for fused, group in variants:
     if base is None:
         base = codes.clone()
     same = bool(torch.equal(codes, base))
-    print(f"fused={fused} group={group} ms/stack={e0.elapsed_time(e1) / 10:.3f} same_codes={same}",
+    print(f"fused={fused} group={group} hints={hints} ms/stack={e0.elapsed_time(e1) / 10:.3f} same_codes={same}",
           {n: round(prof[i], 3) for i, n in enumerate(_lib.PROF_NAMES)}, flush=True)
 
 # where the roles of the fused kernel wait (cycles, averaged over CTAs)

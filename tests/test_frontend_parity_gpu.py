@@ -60,7 +60,13 @@ def test_spectral_stats_match_reference_golden(name):
     g = load_golden(name)
     st = spectral_stats(torch.from_numpy(g["wave"]).cuda()[None], int(g["sr"]))
     assert st.shape == g["stats"].shape
-    np.testing.assert_allclose(st.cpu().numpy(), g["stats"], rtol=2e-4, atol=1e-2)
+    # The stated fp32 tolerance (rtol 2e-4, atol 1e-2 Hz) is each fp32 implementation's distance from the exact
+    # (fp64 oracle) value: the reference's own golden output sits up to 1.6e-4 from it on the pure tone, whose
+    # bandwidth is a sum over leakage tails and amplifies FFT rounding noise. So: within the tolerance of the
+    # oracle, and within twice the tolerance of the reference's fp32 output.
+    exact = mel_oracle.spectral_stats(g["wave"], int(g["sr"]))
+    np.testing.assert_allclose(st.cpu().numpy(), exact, rtol=2e-4, atol=1e-2)
+    np.testing.assert_allclose(st.cpu().numpy(), g["stats"], rtol=4e-4, atol=2e-2)
 
 
 def test_pipeline_fixture_mel():
