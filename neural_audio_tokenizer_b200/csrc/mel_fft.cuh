@@ -71,10 +71,11 @@ __host__ __device__ __forceinline__ void fft16(float2 (&a)[16]) {
     for (int k = 0; k < 8; ++k) { a[k] = cadd(e[k], o[k]); a[k + 8] = csub(e[k], o[k]); }
 }
 
-// Physical slot of logical element i: one pad per 8 and eight more per 128 make all three passes conflict-free.
+// Physical slot of logical element i between the passes: one pad per 8 and eight more per 128 keep the strided
+// accesses of passes 2 and 3 on distinct banks.
 __host__ __device__ __forceinline__ int fft_phys(int i) { return i + (i >> 3) + ((i >> 7) << 3); }
-// Where X[k] lands: k = k1 + 16 k2 + 256 k3  ->  logical k1 * 128 + k2 * 8 + k3.
-__host__ __device__ __forceinline__ int fft_pos(int k) { return fft_phys(((k & 15) << 7) + (((k >> 4) & 15) << 3) + (k >> 8)); }
+// Where X[k] lands after pass 3: natural order with one pad per 16 (pass 3 stores with stride 16).
+__host__ __device__ __forceinline__ int fft_pos(int k) { return k + (k >> 4); }
 // e^{-2 pi i e / 2048} for 0 <= e < 2048 from the half table tw[k] = e^{-2 pi i k / 2048}, k < 1024.
 __host__ __device__ __forceinline__ float2 fft_tw(const float2* tw, int e) {
     const float2 w = tw[e & (NFFT / 2 - 1)];
@@ -96,17 +97,18 @@ __host__ __device__ __forceinline__ void fft_pass2(float2* S, const float2* tw, 
 #pragma unroll
     for (int k = 0; k < 16; ++k) S[fft_phys(s * 128 + k * 8 + n2)] = k == 0 ? a[0] : cmul(a[k], fft_tw(tw, 16 * n2 * k));
 }
-__host__ __device__ __forceinline__ void fft_pass3(float2* S, int t) {
+// Pass 3 reads two length-8 sub-transforms (u = t, t + 128), and, after a team barrier, writes them in natural order:
+// sub-transform u = k1 * 16 + k2 holds X[k1 + 16 k2 + 256 k3], k3 < 8.
+__host__ __device__ __forceinline__ void fft_pass3_load(const float2* S, int t, float2 (&a)[8], float2 (&b)[8]) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int u = t + h * TEAM;
-        float2 a[8];
+    for (int n = 0; n < 8; ++n) { a[n] = S[fft_phys(t * 8 + n)]; b[n] = S[fft_phys((t + TEAM) * 8 + n)]; }
+    fft8(a);
+    fft8(b);
+}
+__host__ __device__ __forceinline__ void fft_pass3_store(float2* S, int t, const float2 (&a)[8], const float2 (&b)[8]) {
+    const int ka = (t >> 4) + 16 * (t & 15), kb = ka + 8;          // u = t + 128 has k1 = (t >> 4) + 8
 #pragma unroll
-        for (int n = 0; n < 8; ++n) a[n] = S[fft_phys(u * 8 + n)];
-        fft8(a);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) S[fft_phys(u * 8 + k)] = a[k];
-    }
+    for (int k3 = 0; k3 < 8; ++k3) { S[fft_pos(ka + 256 * k3)] = a[k3]; S[fft_pos(kb + 256 * k3)] = b[k3]; }
 }
 
 __device__ __forceinline__ float hann_from_tw(const float2* tw, int n) {
@@ -138,26 +140,45 @@ __device__ __forceinline__ float frame_sample(const float* __restrict__ w, long 
     return __ldg(w + j);
 }
 
-// Transform frames a and b (b may not exist) of one clip by one team: S ends up holding the digit-reversed spectrum
-// of a + i b (read it through fft_pos). Ends with a team barrier.
+// Transform frames a and b (b may not exist) of one clip by one team: S ends up holding the spectrum of a + i b in
+// natural order (read it through fft_pos). Ends with a team barrier.
 template <bool SPECTRAL>
-__device__ __forceinline__ void fft_frame_pair(float2* S, const float2* tw_s, const float* __restrict__ wave,
-                                               long long len, long long start_a, bool has_b, long long start_b,
-                                               int team, int t) {
+__device__ __forceinline__ void fft_frame_pair(float2* S, const float2* tw_s, const float* win_s,
+                                               const float* __restrict__ wave, long long len, long long start_a,
+                                               bool has_b, long long start_b, int team, int t) {
     float2 a[16];
+    const long long shift = SPECTRAL ? 0 : NFFT / 2;
+    const long long last = (has_b ? start_b : start_a) - shift + NFFT - 1;
+    if (has_b && start_a - shift >= 0 && last < len) {
+        // both frames lie inside the clip (all but the first and last few): plain coalesced loads, all in flight
+        const float* pa = wave + (start_a - shift) + t;
+        const float* pb = wave + (start_b - shift) + t;
+        float va[16], vb[16];
 #pragma unroll
-    for (int n = 0; n < 16; ++n) {
-        const int idx = n * TEAM + t;
-        const float wn = hann_from_tw(tw_s, idx);
-        const float va = frame_sample<SPECTRAL>(wave, len, start_a + idx) * wn;
-        const float vb = has_b ? frame_sample<SPECTRAL>(wave, len, start_b + idx) * wn : 0.f;
-        a[n] = make_float2(va, vb);
+        for (int n = 0; n < 16; ++n) { va[n] = __ldg(pa + n * TEAM); vb[n] = __ldg(pb + n * TEAM); }
+#pragma unroll
+        for (int n = 0; n < 16; ++n) {
+            const float wn = win_s[n * TEAM + t];
+            a[n] = make_float2(va[n] * wn, vb[n] * wn);
+        }
+    } else {
+#pragma unroll
+        for (int n = 0; n < 16; ++n) {
+            const int idx = n * TEAM + t;
+            const float wn = win_s[idx];
+            const float va = frame_sample<SPECTRAL>(wave, len, start_a + idx) * wn;
+            const float vb = has_b ? frame_sample<SPECTRAL>(wave, len, start_b + idx) * wn : 0.f;
+            a[n] = make_float2(va, vb);
+        }
     }
     fft_pass1(S, tw_s, t, a);
     team_sync(team);
     fft_pass2(S, tw_s, t);
     team_sync(team);
-    fft_pass3(S, t);
+    float2 ra[8], rb[8];
+    fft_pass3_load(S, t, ra, rb);
+    team_sync(team);
+    fft_pass3_store(S, t, ra, rb);
     team_sync(team);
 }
 
@@ -169,19 +190,40 @@ __device__ __forceinline__ void split_bins(const float2* S, int k, float2& xa, f
     xb = make_float2(0.5f * (z.y + y.y), 0.5f * (y.x - z.x));
 }
 
-__global__ void __launch_bounds__(THREADS)
+constexpr int FB_PACK_CAP = 2304;            // non-zero filterbank weights staged in shared memory (HTK, 128 bands: ~2000)
+
+__global__ void __launch_bounds__(THREADS, 3)
 mel_power_kernel(MelArgs p, long long groups_per_clip, long long total_groups) {
     extern __shared__ __align__(16) unsigned char fe_smem[];
     float2* tw_s = reinterpret_cast<float2*>(fe_smem);                               // [NFFT / 2]
     float2* S_all = tw_s + NFFT / 2;                                                  // [2][FFT_BUF]
-    float* pw_all = reinterpret_cast<float*>(S_all + 2 * FFT_BUF);                    // [2][2][NBINS + 3]
-    float* out_tile = pw_all + 4 * (NBINS + 3);                                       // [n_mels][FRAMES_PER_CTA + 1]
+    float* win_s = reinterpret_cast<float*>(S_all + 2 * FFT_BUF);                     // [NFFT]
+    float* wpack = win_s + NFFT;                                                      // [FB_PACK_CAP]
+    int* woff = reinterpret_cast<int*>(wpack + FB_PACK_CAP);                          // [MAX_MELS + 1]
+    float* out_tile = reinterpret_cast<float*>(woff + MAX_MELS + 1);                  // [n_mels][FRAMES_PER_CTA + 1]
     const int team = threadIdx.x / TEAM, t = threadIdx.x % TEAM;
     float2* S = S_all + team * FFT_BUF;
-    float* pw0 = pw_all + team * 2 * (NBINS + 3);
+    // the transform buffer is dead once the bins are split: the two power spectra of the pair live in it afterwards
+    float* pw0 = reinterpret_cast<float*>(S);
     float* pw1 = pw0 + NBINS + 3;
     for (int i = threadIdx.x; i < NFFT / 2; i += THREADS) tw_s[i] = p.tw[i];
+    if (threadIdx.x == 0) {
+        int off = 0;
+        for (int m = 0; m < p.n_mels; ++m) { woff[m] = off; const int2 be = p.band[m]; off += max(0, be.y - be.x); }
+        woff[p.n_mels] = off;
+    }
     __syncthreads();
+    for (int i = threadIdx.x; i < NFFT; i += THREADS) win_s[i] = hann_from_tw(tw_s, i);
+    const bool packed = woff[p.n_mels] <= FB_PACK_CAP;          // a dense user filterbank falls back to global reads
+    if (packed) {
+        for (int m = 0; m < p.n_mels; ++m) {
+            const int2 be = p.band[m];
+            for (int k = be.x + threadIdx.x; k < be.y; k += THREADS)
+                wpack[woff[m] + k - be.x] = p.fbT[static_cast<long long>(m) * NBINS + k];
+        }
+    }
+    __syncthreads();
+    const int quad = t & 3;
     for (long long grp = blockIdx.x; grp < total_groups; grp += gridDim.x) {
         const long long b = grp / groups_per_clip;
         const long long f0 = (grp - b * groups_per_clip) * FRAMES_PER_CTA;
@@ -191,22 +233,41 @@ mel_power_kernel(MelArgs p, long long groups_per_clip, long long total_groups) {
         for (int pr = team * 4; pr < team * 4 + 4; pr += 2) {
             if (pr >= nf) break;                                                      // team-uniform
             const bool has_b = pr + 1 < nf;
-            fft_frame_pair<false>(S, tw_s, wave, p.S, (f0 + pr) * p.hop, has_b, (f0 + pr + 1) * p.hop, team, t);
-            for (int k = t; k < NBINS; k += TEAM) {
-                float2 xa, xb;
-                split_bins(S, k, xa, xb);
-                pw0[k] = (xa.x * xa.x + xa.y * xa.y) * p.inv_wsum;
-                pw1[k] = (xb.x * xb.x + xb.y * xb.y) * p.inv_wsum;
+            fft_frame_pair<false>(S, tw_s, win_s, wave, p.S, (f0 + pr) * p.hop, has_b, (f0 + pr + 1) * p.hop, team, t);
+            float pa[9], pb[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+                const int k = t + q * TEAM;
+                if (k < NBINS) {
+                    float2 xa, xb;
+                    split_bins(S, k, xa, xb);
+                    pa[q] = (xa.x * xa.x + xa.y * xa.y) * p.inv_wsum;
+                    pb[q] = (xb.x * xb.x + xb.y * xb.y) * p.inv_wsum;
+                }
             }
             team_sync(team);
-            for (int o = t; o < 2 * p.n_mels; o += TEAM) {
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+                const int k = t + q * TEAM;
+                if (k < NBINS) { pw0[k] = pa[q]; pw1[k] = pb[q]; }
+            }
+            team_sync(team);
+            // banded projection: four lanes per (frame, band), taps interleaved, fixed-order quad reduction
+            for (int o = t >> 2; o < 2 * p.n_mels; o += TEAM / 4) {
                 const int which = o / p.n_mels, m = o - which * p.n_mels;
-                const int2 be = __ldg(&p.band[m]);
-                const float* fb = p.fbT + static_cast<long long>(m) * NBINS;
+                const int2 be = p.band[m];
                 const float* pw = which ? pw1 : pw0;
                 float acc = 0.f;
-                for (int k = be.x; k < be.y; ++k) acc = fmaf(pw[k], __ldg(fb + k), acc);
-                out_tile[m * (FRAMES_PER_CTA + 1) + pr + which] = acc;
+                if (packed) {
+                    const float* wv = wpack + woff[m] - be.x;
+                    for (int k = be.x + quad; k < be.y; k += 4) acc = fmaf(pw[k], wv[k], acc);
+                } else {
+                    const float* fb = p.fbT + static_cast<long long>(m) * NBINS;
+                    for (int k = be.x + quad; k < be.y; k += 4) acc = fmaf(pw[k], __ldg(fb + k), acc);
+                }
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                if (quad == 0) out_tile[m * (FRAMES_PER_CTA + 1) + pr + which] = acc;
             }
             team_sync(team);
         }
@@ -224,7 +285,8 @@ mel_power_kernel(MelArgs p, long long groups_per_clip, long long total_groups) {
     }
 }
 constexpr size_t mel_smem_bytes(int n_mels) {
-    return sizeof(float2) * (NFFT / 2 + 2 * FFT_BUF) + sizeof(float) * (4 * (NBINS + 3) + n_mels * (FRAMES_PER_CTA + 1));
+    return sizeof(float2) * (NFFT / 2 + 2 * FFT_BUF) + sizeof(float) * (NFFT + FB_PACK_CAP) + sizeof(int) * (MAX_MELS + 1) +
+           sizeof(float) * n_mels * (FRAMES_PER_CTA + 1);
 }
 
 struct SpectralArgs {
@@ -247,30 +309,43 @@ __device__ __forceinline__ float team_sum(float v, float* sh, int team, int t) {
     return r;
 }
 
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 3)
 spectral_stats_kernel(SpectralArgs p) {
     extern __shared__ __align__(16) unsigned char fe_smem[];
     float2* tw_s = reinterpret_cast<float2*>(fe_smem);                               // [NFFT / 2]
     float2* S_all = tw_s + NFFT / 2;                                                  // [2][FFT_BUF]
-    float* mag_all = reinterpret_cast<float*>(S_all + 2 * FFT_BUF);                   // [2][2][NBINS + 3]
+    float* win_s = reinterpret_cast<float*>(S_all + 2 * FFT_BUF);                     // [NFFT]
     __shared__ float red[8];
     const int team = threadIdx.x / TEAM, t = threadIdx.x % TEAM;
     float2* S = S_all + team * FFT_BUF;
-    float* mag0 = mag_all + team * 2 * (NBINS + 3);
+    float* mag0 = reinterpret_cast<float*>(S);         // the transform buffer is dead once the bins are split
     float* mag1 = mag0 + NBINS + 3;
     for (int i = threadIdx.x; i < NFFT / 2; i += THREADS) tw_s[i] = p.tw[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < NFFT; i += THREADS) win_s[i] = hann_from_tw(tw_s, i);
     __syncthreads();
     const long long pairs = (p.T + 1) / 2;
     // one frame pair per team and iteration
     for (long long pr = static_cast<long long>(blockIdx.x) * 2 + team; pr < pairs; pr += static_cast<long long>(gridDim.x) * 2) {
         const long long fa = 2 * pr, fb = fa + 1;
         const bool has_b = fb < p.T;
-        fft_frame_pair<true>(S, tw_s, p.wave, p.S, fa * p.hop, has_b, fb * p.hop, team, t);
-        for (int k = t; k < NBINS; k += TEAM) {
-            float2 xa, xb;
-            split_bins(S, k, xa, xb);
-            mag0[k] = sqrtf(xa.x * xa.x + xa.y * xa.y) + 1e-12f;          // nat.py:2418
-            mag1[k] = sqrtf(xb.x * xb.x + xb.y * xb.y) + 1e-12f;
+        fft_frame_pair<true>(S, tw_s, win_s, p.wave, p.S, fa * p.hop, has_b, fb * p.hop, team, t);
+        float ma[9], mb[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+            const int k = t + q * TEAM;
+            if (k < NBINS) {
+                float2 xa, xb;
+                split_bins(S, k, xa, xb);
+                ma[q] = sqrtf(xa.x * xa.x + xa.y * xa.y) + 1e-12f;          // nat.py:2418
+                mb[q] = sqrtf(xb.x * xb.x + xb.y * xb.y) + 1e-12f;
+            }
+        }
+        team_sync(team);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+            const int k = t + q * TEAM;
+            if (k < NBINS) { mag0[k] = ma[q]; mag1[k] = mb[q]; }
         }
         team_sync(team);
         for (int which = 0; which < 2; ++which) {
@@ -299,9 +374,7 @@ spectral_stats_kernel(SpectralArgs p) {
         team_sync(team);
     }
 }
-constexpr size_t spectral_smem_bytes() {
-    return sizeof(float2) * (NFFT / 2 + 2 * FFT_BUF) + sizeof(float) * 4 * (NBINS + 3);
-}
+constexpr size_t spectral_smem_bytes() { return sizeof(float2) * (NFFT / 2 + 2 * FFT_BUF) + sizeof(float) * NFFT; }
 
 // dense [NBINS, n_mels] filterbank -> band-major copy + per-band non-zero range (one CTA per band)
 __global__ void __launch_bounds__(128)

@@ -1,4 +1,4 @@
-// Host-side check of the 16 x 16 x 8 transform in csrc/mel_fft.cuh: the three passes are replayed serially over the
+// Host-side check of the 16 x 16 x 8 transform in csrc/mel_fft.cuh: the passes are replayed serially over the
 // 128 "threads" of a team and compared with a direct double-precision DFT. Built and run by tests/test_host_fft.py.
 #include <cmath>
 #include <cstdio>
@@ -24,7 +24,17 @@ int main() {
         fft_pass1(S.data(), tw.data(), t, a);
     }
     for (int t = 0; t < TEAM; ++t) fft_pass2(S.data(), tw.data(), t);
-    for (int t = 0; t < TEAM; ++t) fft_pass3(S.data(), t);
+    std::vector<float2> ra(TEAM * 8), rb(TEAM * 8);
+    for (int t = 0; t < TEAM; ++t) {
+        float2 a[8], b[8];
+        fft_pass3_load(S.data(), t, a, b);
+        for (int i = 0; i < 8; ++i) { ra[t * 8 + i] = a[i]; rb[t * 8 + i] = b[i]; }
+    }
+    for (int t = 0; t < TEAM; ++t) {               // (a team barrier separates the loads from the stores on the device)
+        float2 a[8], b[8];
+        for (int i = 0; i < 8; ++i) { a[i] = ra[t * 8 + i]; b[i] = rb[t * 8 + i]; }
+        fft_pass3_store(S.data(), t, a, b);
+    }
     double max_err = 0.0, max_ref = 0.0;
     std::vector<char> used(FFT_BUF, 0);
     for (int k = 0; k < NFFT; ++k) {
