@@ -157,6 +157,25 @@ int64_t nat_mel_num_frames(int64_t S, int hop);                       /* 1 + S/h
 int64_t nat_spectral_num_frames(int64_t S, int n_fft, int hop);       /* nat.py:2400-2403                      */
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * NDJSON emission (host code)
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* Every line between the header event and the end event of the reference's NDJSON stream, byte for byte:
+ * replaces the per-frame loop of StreamingProtocol.create_ndjson_stream (nat.py:4482-4513) and
+ * NDJSONStreamer.create_frame (nat.py:2722-2836), plus the final flush of create_end_marker (nat.py:2843-2845).
+ *   sem_codes_host / ac_codes_host   HOST index streams [n_sem][ld_frames] / [n_ac][ld_frames] of `code_dtype`
+ *   rle_mode                          StreamingProtocol.rle_mode
+ *   layer_is_rle                      [n_sem + n_ac] bytes, 1 where NDJSONStreamer._should_use_rle_for_layer(name)
+ *                                     (nat.py:2707-2711) is true; required when rle_mode != 0
+ *   text_out / len_out                malloc'ed text (lines joined by '\n', no trailing newline; empty when there
+ *                                     is nothing to emit); release with nat_free_host() */
+int nat_ndjson_emit_frames(const void* sem_codes_host, const void* ac_codes_host, int code_dtype, int n_sem, int n_ac,
+                           int64_t ld_frames, int64_t num_frames, int sample_rate, int hop_length, int rle_mode,
+                           const unsigned char* layer_is_rle, double keyframe_interval_seconds, char** text_out,
+                           size_t* len_out);
+void nat_free_host(void* p);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Debug / validation hooks (used by tests/; not part of the drop-in surface)
  * ------------------------------------------------------------------------------------------------------------- */
 

@@ -23,7 +23,7 @@ NVCC_FLAGS = [
 
 
 def sources():
-    return [os.path.join(CSRC, "nat_b200.cu")]
+    return [os.path.join(CSRC, "nat_b200.cu"), os.path.join(CSRC, "ndjson_emit.cpp")]
 
 
 def _stale() -> bool:
