@@ -157,6 +157,36 @@ bool carve(void* base, size_t bytes, int dp, int L, long long want_rows, Workspa
 
 }  // namespace
 
+template <int NV>
+static cudaError_t stack_kernel_attrs() {
+    cudaError_t e = cudaFuncSetAttribute(nat::stack::rvq_stack_kernel<NV, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         nat::stack::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(nat::stack::rvq_stack_kernel<NV, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                nat::stack::SMEM_BYTES);
+}
+
+// One persistent launch of the fused stack kernel: plain grid (pair == 1) or clusters of two CTAs (pair == 2).
+template <int NV>
+static cudaError_t launch_stack(int pair, int grid, cudaStream_t st, const CUtensorMap& map_a, const CUtensorMap& map_b,
+                                const nat::stack::StackArgs& sa) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(nat::stack::NUM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = nat::stack::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = pair;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (pair == 2) return cudaLaunchKernelEx(&cfg, nat::stack::rvq_stack_kernel<NV, 2>, map_a, map_b, sa);
+    return cudaLaunchKernelEx(&cfg, nat::stack::rvq_stack_kernel<NV, 1>, map_a, map_b, sa);
+}
+
 struct nat_rvq_codebooks {
     int L, K, D, dp, kp, device, sm_count;
     float* cbf;                       // [L, K, dp]
@@ -165,7 +195,8 @@ struct nat_rvq_codebooks {
     double* cn64;                     // [L, K]
     nat::rows::LayerConst* lc;        // [L]
     int* scratch;                     // [L, kScratchPerLayer]
-    CUtensorMap map_b;
+    CUtensorMap map_b;                // box 64 x 256 codes
+    CUtensorMap map_b_half;           // box 64 x 128 codes: the half of a B tile one CTA of a pair stages
     unsigned long long* stack_dbg;    // [sm_count][DBG_SLOTS] cycle counters of the last fused launch (debug hook)
     bool stack_dbg_on;
     // staging arena of the host-buffer entry point (grown on first use)
@@ -248,19 +279,16 @@ int nat_rvq_codebooks_create(const float* const* codebooks_dev, int L, int K, in
     if (rc == NAT_OK) guard(cudaMemsetAsync(cb->cbh, 0, n_h * 2, st), "cudaMemsetAsync(cbh)");
     if (rc == NAT_OK) rc = upload_codebooks(cb, codebooks_dev, st);
     if (rc == NAT_OK) rc = make_map_f16(&cb->map_b, cb->cbh, static_cast<long long>(L) * cb->kp, cb->dp, 256);
+    if (rc == NAT_OK) rc = make_map_f16(&cb->map_b_half, cb->cbh, static_cast<long long>(L) * cb->kp, cb->dp, 128);
     if (rc == NAT_OK) {
         guard(cudaFuncSetAttribute(nat::gemm::rvq_gemm_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    nat::gemm::SMEM_BYTES), "cudaFuncSetAttribute");
         guard(cudaFuncSetAttribute(nat::gemm::rvq_gemm_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    nat::gemm::SMEM_BYTES), "cudaFuncSetAttribute");
-        guard(cudaFuncSetAttribute(nat::stack::rvq_stack_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   nat::stack::SMEM_BYTES), "cudaFuncSetAttribute");
-        guard(cudaFuncSetAttribute(nat::stack::rvq_stack_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   nat::stack::SMEM_BYTES), "cudaFuncSetAttribute");
-        guard(cudaFuncSetAttribute(nat::stack::rvq_stack_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   nat::stack::SMEM_BYTES), "cudaFuncSetAttribute");
-        guard(cudaFuncSetAttribute(nat::stack::rvq_stack_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   nat::stack::SMEM_BYTES), "cudaFuncSetAttribute");
+        guard(stack_kernel_attrs<2>(), "cudaFuncSetAttribute");
+        guard(stack_kernel_attrs<4>(), "cudaFuncSetAttribute");
+        guard(stack_kernel_attrs<6>(), "cudaFuncSetAttribute");
+        guard(stack_kernel_attrs<8>(), "cudaFuncSetAttribute");
         guard(cudaFuncSetAttribute(nat::rows::prep_bct_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    200 * 1024), "cudaFuncSetAttribute");
     }
@@ -333,10 +361,14 @@ static bool fused_enabled() {
     const char* e = getenv("NAT_RVQ_FUSED");         // read every call: tests flip it to cross-check both paths
     return e == nullptr || atoi(e) != 0;
 }
-static int fused_group() {
+static bool fused_pair() {
+    const char* e = getenv("NAT_RVQ_PAIR");
+    return e == nullptr || atoi(e) != 1;
+}
+static int fused_group(int pair) {
     const char* e = getenv("NAT_RVQ_GROUP");
     const int v = e ? atoi(e) : 0;
-    return v >= 1 ? v : 2;
+    return v >= 1 ? v : (pair == 2 ? 3 : 2);      // measured on B200: 270k x 768, K = 1024 (profiles/)
 }
 
 // Everything one chunk of frames [n0, n0 + n) needs, in order, on one stream.
@@ -365,17 +397,23 @@ static int encode_chunk(const EncodeCall& c, const Workspace& ws, const CUtensor
         sa.stats = c.stats;
         sa.n_rows = n; sa.n_tiles = n_tiles; sa.L = cb->L; sa.K = cb->K; sa.kp = cb->kp; sa.dp = cb->dp;
         sa.code_dtype = c.code_dtype;
-        sa.group = fused_group();
         sa.dbg = cb->stack_dbg_on ? cb->stack_dbg : nullptr;
         { const char* e = getenv("NAT_RVQ_DBG_MODE"); sa.dbg_mode = e ? atoi(e) : 0; }
-        const int grid = std::min(n_tiles, cb->sm_count);
+        // CTA pairs (one tcgen05.mma.cta_group::2 per two SMs) once there is more than one tile; NAT_RVQ_PAIR=1 keeps
+        // the single-CTA form for A/B measurements.
+        const int pair = (n_tiles >= 2 && cb->sm_count >= 2 && fused_pair()) ? 2 : 1;
+        const int grid = pair == 2 ? std::min((n_tiles + 1) & ~1, cb->sm_count & ~1) : std::min(n_tiles, cb->sm_count);
+        const CUtensorMap& map_b = pair == 2 ? cb->map_b_half : cb->map_b;
+        sa.group = fused_group(pair);
         const int nv = (cb->dp / 4 + 31) / 32;
+        cudaError_t le = cudaSuccess;
         NAT_LAUNCH(1, st, {
-            if (nv <= 2) stack::rvq_stack_kernel<2><<<grid, stack::NUM_THREADS, stack::SMEM_BYTES, st>>>(map_a, cb->map_b, sa);
-            else if (nv <= 4) stack::rvq_stack_kernel<4><<<grid, stack::NUM_THREADS, stack::SMEM_BYTES, st>>>(map_a, cb->map_b, sa);
-            else if (nv <= 6) stack::rvq_stack_kernel<6><<<grid, stack::NUM_THREADS, stack::SMEM_BYTES, st>>>(map_a, cb->map_b, sa);
-            else stack::rvq_stack_kernel<8><<<grid, stack::NUM_THREADS, stack::SMEM_BYTES, st>>>(map_a, cb->map_b, sa);
+            if (nv <= 2) le = launch_stack<2>(pair, grid, st, map_a, map_b, sa);
+            else if (nv <= 4) le = launch_stack<4>(pair, grid, st, map_a, map_b, sa);
+            else if (nv <= 6) le = launch_stack<6>(pair, grid, st, map_a, map_b, sa);
+            else le = launch_stack<8>(pair, grid, st, map_a, map_b, sa);
         });
+        NAT_CUDA(le);
         NAT_CUDA(cudaGetLastError());
         if (c.want_loss)
             for (int l = 0; l < cb->L; ++l)

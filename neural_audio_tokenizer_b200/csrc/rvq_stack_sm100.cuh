@@ -60,15 +60,26 @@ constexpr int LCAP = 16;         // eight-code groups listed per frame (compacte
 constexpr int HCAP = 7;          // candidates handed to the update warps per frame
 constexpr unsigned HAND_SCAN = 0xFFFFu;
 
-constexpr int OFF_A = 0;
-constexpr int OFF_B = OFF_A + STAGES * A_STAGE_BYTES;
-constexpr int OFF_LIST_S = OFF_B + STAGES * B_STAGE_BYTES;
-constexpr int OFF_LIST_I = OFF_LIST_S + LCAP * BLOCK_M * 4;
-constexpr int OFF_HAND = OFF_LIST_I + LCAP * BLOCK_M * 4;
-constexpr int OFF_CN = OFF_HAND + 2 * BLOCK_M * 16;          // [2][BLOCK_N] ||c||^2 of the chunk being scored / the next
-constexpr int OFF_BARS = OFF_CN + 2 * BLOCK_N * 4;
-constexpr int SMEM_BYTES = OFF_BARS + 256 + 1024 /*alignment slack*/;
-static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+#ifndef NAT_STAGES_PAIR
+#define NAT_STAGES_PAIR 6
+#endif
+// Shared-memory carve-up. A CTA of a pair stages half of every B tile, so the same bytes buy a deeper ring.
+template <int PAIR>
+struct Smem {
+    static constexpr int STAGES = PAIR == 2 ? NAT_STAGES_PAIR : nat::stack::STAGES;
+    static constexpr int B_BYTES = B_STAGE_BYTES / PAIR;          // bytes of a B stage held by one CTA
+    static constexpr int OFF_A = 0;
+    static constexpr int OFF_B = OFF_A + STAGES * A_STAGE_BYTES;
+    static constexpr int OFF_LIST_S = OFF_B + STAGES * B_BYTES;
+    static constexpr int OFF_LIST_I = OFF_LIST_S + LCAP * BLOCK_M * 4;
+    static constexpr int OFF_HAND = OFF_LIST_I + LCAP * BLOCK_M * 4;
+    static constexpr int OFF_CN = OFF_HAND + 2 * BLOCK_M * 16;    // [2][BLOCK_N] ||c||^2 of the chunk being scored / the next
+    static constexpr int OFF_BARS = OFF_CN + 2 * BLOCK_N * 4;
+    static constexpr int BYTES = OFF_BARS + 256 + 1024 /*alignment slack*/;
+    static_assert(BYTES <= 227 * 1024, "shared memory budget");
+    static_assert((2 * STAGES + 8) * 8 + 4 + UPD_WARPS * 4 <= 256, "barrier block");
+};
+constexpr int SMEM_BYTES = Smem<1>::BYTES > Smem<2>::BYTES ? Smem<1>::BYTES : Smem<2>::BYTES;
 
 struct StackArgs {
     const float* cbf;            // [L, K, dp] fp32 codebooks, zero padded
@@ -180,11 +191,26 @@ __device__ __forceinline__ void load_code(float4 (&cv)[NV], const float4* __rest
 // a - b on both halves, rounded exactly like two __fsub_rn (one fused multiply by -1, one rounding)
 __device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
 
-template <int NV>
+// PAIR = 1: one CTA per tile, tcgen05.mma.cta_group::1 (M 128 x N 256).
+// PAIR = 2: launched as clusters of two CTAs (the two SMs of a TPC). Each CTA still owns its own 128-frame tiles,
+//   candidate lists, update warps and accumulators, but the pair runs ONE tcgen05.mma.cta_group::2 (M 256 x N 256)
+//   issued by the even CTA: each CTA stages only the 128 codes x 64 half of every B tile, so the codebook traffic
+//   from L2 per frame halves. Both CTAs walk the same number of jobs (the odd CTA may end on a phantom tile whose
+//   frames are all out of range). Cross-CTA protocol: both TMA producers signal the leader's `full` barrier, the
+//   leader's commits arrive on `empty` / `tfull` in both CTAs, both candidate warpgroups arrive on the leader's
+//   `tempty`.
+template <int NV, int PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp], box 64 x 128, SWIZZLE_128B
-                 const __grid_constant__ CUtensorMap map_b,   // fp16 [L*kp, dp], box 64 x 256, SWIZZLE_128B
+                 const __grid_constant__ CUtensorMap map_b,   // fp16 [L*kp, dp], box 64 x (256 / PAIR), SWIZZLE_128B
                  const __grid_constant__ StackArgs p) {
+    static_assert(PAIR == 1 || PAIR == 2, "one CTA or a CTA pair");
+    using SM = Smem<PAIR>;
+    constexpr int STAGES = SM::STAGES, B_BYTES = SM::B_BYTES;
+    constexpr int OFF_A = SM::OFF_A, OFF_B = SM::OFF_B, OFF_LIST_S = SM::OFF_LIST_S, OFF_LIST_I = SM::OFF_LIST_I,
+                  OFF_HAND = SM::OFF_HAND, OFF_CN = SM::OFF_CN, OFF_BARS = SM::OFF_BARS;
+    const uint32_t crank = PAIR == 2 ? cluster_ctarank() : 0u;
+    const bool leader = crank == 0;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem + OFF_A;
@@ -206,7 +232,8 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
     const int lane = threadIdx.x & 31;
     const int n_chunks = p.kp / BLOCK_N;
     const int n_kblocks = p.dp / BLOCK_K;
-    const int my_tiles = (p.n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+    // PAIR = 2: both CTAs take the leader's count, so the odd CTA may run one phantom tile (index >= n_tiles)
+    const int my_tiles = (p.n_tiles - static_cast<int>(blockIdx.x - crank) + static_cast<int>(gridDim.x) - 1) /
                          static_cast<int>(gridDim.x);
     const int group = max(1, p.group);
 
@@ -216,17 +243,19 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], EPI_WARPS);
+            mbar_init(&tempty[i], EPI_WARPS * PAIR);
             mbar_init(&cfull[i], EPI_WARPS);
             mbar_init(&cempty[i], UPD_WARPS);
         }
         for (int i = 0; i < UPD_WARPS; ++i) ready[i] = 0;
         fence_mbar_init();
     } else if (warp == WARP_MMA) {
-        tmem_alloc(tmem_slot, TMEM_COLS);
+        if (PAIR == 2) tmem_alloc_pair(tmem_slot, TMEM_COLS);
+        else tmem_alloc(tmem_slot, TMEM_COLS);
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if (PAIR == 2) cluster_sync_all();      // the peer's barriers must exist before anything arrives on them
+    else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -244,7 +273,8 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
             const int gs = min(group, my_tiles - g0);
             for (int l = 0; l < p.L; ++l) {
                 for (int i = g0; i < g0 + gs; ++i, ++job) {
-                    const int tile = blockIdx.x + i * gridDim.x;
+                    // a phantom tile re-reads the last real tile's operand (its results are never used)
+                    const int tile = min(static_cast<int>(blockIdx.x + i * gridDim.x), p.n_tiles - 1);
                     if (l > 0) {
                         const long long t0 = w_ready.begin();
                         // operand rows of (tile, l) are written by this CTA's update warps in job (tile, l-1):
@@ -260,10 +290,21 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
                                 const long long t1 = w_empty.begin();
                                 mbar_wait(&empty[s], ph ^ 1);
                                 w_empty.end(t1);
-                                mbar_arrive_expect_tx(&full[s], A_STAGE_BYTES + B_STAGE_BYTES);
-                                tma_load_2d(smem_a + s * A_STAGE_BYTES, &map_a, &full[s], kb * BLOCK_K, tile * BLOCK_M);
-                                tma_load_2d(smem_b + s * B_STAGE_BYTES, &map_b, &full[s], kb * BLOCK_K,
-                                            l * p.kp + chunk * BLOCK_N);
+                                if (PAIR == 2) {
+                                    // both CTAs' bytes are counted on the leader's barrier
+                                    const bool skip_a = (p.dbg_mode & 16) && chunk > 0;      // timing experiment only
+                                    if (leader) mbar_arrive_expect_tx(&full[s], 2 * ((skip_a ? 0 : A_STAGE_BYTES) + B_BYTES));
+                                    const uint32_t bar = mapa_rank(smem_u32(&full[s]), 0);
+                                    if (!skip_a)
+                                    tma_load_2d_pair(smem_a + s * A_STAGE_BYTES, &map_a, bar, kb * BLOCK_K, tile * BLOCK_M);
+                                    tma_load_2d_pair(smem_b + s * B_BYTES, &map_b, bar, kb * BLOCK_K,
+                                                     l * p.kp + chunk * BLOCK_N + crank * (BLOCK_N / 2));
+                                } else {
+                                    mbar_arrive_expect_tx(&full[s], A_STAGE_BYTES + B_BYTES);
+                                    tma_load_2d(smem_a + s * A_STAGE_BYTES, &map_a, &full[s], kb * BLOCK_K, tile * BLOCK_M);
+                                    tma_load_2d(smem_b + s * B_BYTES, &map_b, &full[s], kb * BLOCK_K,
+                                                l * p.kp + chunk * BLOCK_N);
+                                }
                                 if (++s == STAGES) { s = 0; ph ^= 1; }
                             }
                         }
@@ -280,8 +321,8 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
         }
     } else if (warp == WARP_MMA) {
         // ------------------------------------------------------------------ MMA issuer (one thread)
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_f16_f32(BLOCK_M, BLOCK_N);
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc = umma_idesc_f16_f32(BLOCK_M * PAIR, BLOCK_N);
             uint32_t s = 0, ph = 0;
             const int total = p.L * my_tiles * n_chunks;
             WaitClock w_tempty(p.dbg != nullptr), w_full(p.dbg != nullptr);
@@ -298,12 +339,19 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
                     w_full.end(t1);
                     tcgen05_fence_after();
                     const uint64_t adesc = umma_desc_kmajor_sw128(smem_a + s * A_STAGE_BYTES);
-                    const uint64_t bdesc = umma_desc_kmajor_sw128(smem_b + s * B_STAGE_BYTES);
+                    const uint64_t bdesc = umma_desc_kmajor_sw128(smem_b + s * B_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                        umma_f16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-                    umma_commit(&empty[s]);
-                    if (kb == n_kblocks - 1) umma_commit(&tfull[as]);
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        if (PAIR == 2) umma_f16_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        else umma_f16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    if (PAIR == 2) {
+                        umma_commit_pair(&empty[s]);
+                        if (kb == n_kblocks - 1) umma_commit_pair(&tfull[as]);
+                    } else {
+                        umma_commit(&empty[s]);
+                        if (kb == n_kblocks - 1) umma_commit(&tfull[as]);
+                    }
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
@@ -435,7 +483,7 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
                             for (int g = 0; g < BLOCK_N / 32; ++g) {
                                 tmem_ld_32x32b_x32(taddr + g * 32, va);
                                 { const long long tw = w_ld.begin(); tmem_wait_ld(); w_ld.end(tw); }
-                                if (p.dbg_mode < 6) scan32(va, g, false);
+                                if ((p.dbg_mode & 15) < 6) scan32(va, g, false);
                             }
                             if (valid) thr = fmaf(fabsf(m) + window, 2.4e-7f, m + window);
                         }
@@ -443,12 +491,15 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
                         for (int g = 0; g < BLOCK_N / 32; ++g) {
                             tmem_ld_32x32b_x32(taddr + g * 32, va);
                             { const long long tw = w_ld.begin(); tmem_wait_ld(); w_ld.end(tw); }
-                            if (p.dbg_mode < 6) scan32(va, g, true);
+                            if ((p.dbg_mode & 15) < 6) scan32(va, g, true);
                         }
                         // accumulator stage drained: hand it back to the MMA warp
                         tcgen05_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&tempty[as]);
+                        if (lane == 0) {
+                            if (PAIR == 2) mbar_arrive_cluster(mapa_rank(smem_u32(&tempty[as]), 0));
+                            else mbar_arrive(&tempty[as]);
+                        }
                         sts_f32x2(cnbuf + ((it + 1) & 1) * (BLOCK_N * 4) + tid * 8, cn_next);
                     }
                     // hand the survivors to the update warps: u16 count + up to HCAP u16 code indices per frame
@@ -470,7 +521,7 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
                             ++n;
                         }
                     }
-                    if (p.dbg_mode >= 6) { n = 1; sts_u16(hrec + 2, 0); overflow = false; }
+                    if ((p.dbg_mode & 15) >= 6) { n = 1; sts_u16(hrec + 2, 0); overflow = false; }
                     if (!valid) n = 0;
                     else if (overflow || n == 0 || n > HCAP) n = HAND_SCAN;
                     sts_u16(hrec, static_cast<unsigned short>(n));
@@ -532,7 +583,7 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
                     if (lane < ROWS_PER_UPD_WARP) rec = hand[slot * BLOCK_M + uw * ROWS_PER_UPD_WARP + lane];
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&cempty[slot]);
-                    if (p.dbg_mode == 3 || p.dbg_mode == 7) {
+                    if ((p.dbg_mode & 15) == 3 || (p.dbg_mode & 15) == 7) {
                         __syncwarp();
                         if (lane == 0) st_release(&ready[uw], job + 1);
                         continue;
@@ -729,10 +780,12 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
     }
 
     tcgen05_fence_before();
-    __syncthreads();
+    if (PAIR == 2) cluster_sync_all();      // neither CTA may leave while the other can still reach into it
+    else __syncthreads();
     if (warp == WARP_MMA) {
         tcgen05_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        if (PAIR == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+        else tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
