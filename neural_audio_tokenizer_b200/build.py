@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libnat_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
-    "-shared", "-Xcompiler", "-fPIC",
+    "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread",
     "-Xptxas", "-v",
     "--expt-relaxed-constexpr",
 ]

@@ -79,3 +79,5 @@ def patch_reference_module(nat_module) -> None:
     shim = types.SimpleNamespace(**{k: getattr(nat_module.T, k) for k in dir(nat_module.T) if not k.startswith("_")})
     shim.MelSpectrogram = MelSpectrogram
     nat_module.T = shim
+    from . import ndjson
+    ndjson.install(nat_module)                      # StreamingProtocol.create_ndjson_stream -> native emitter

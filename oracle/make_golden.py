@@ -155,10 +155,65 @@ def pipeline_case(nat, name: str):
     print(f"{name}: {len(frames)} frames, first S={frames[0]['S']} A={frames[0]['A']}")
 
 
+NDJSON_CASES = [
+    # name, sr, hop, rle, per_layer_encoding, keyframe interval, frames, stickiness of (semantic, acoustic) streams
+    ("dense_22050", 22050, 512, False, None, 5.0, 200, (0.0, 0.0)),
+    ("dense_16000_exact_ms", 16000, 320, False, None, 5.0, 60, (0.0, 0.0)),
+    ("rle_default_keyframes", 22050, 512, True, None, 5.0, 1500, (0.9, 0.0)),
+    ("rle_per_layer_24000", 24000, 320, True, {"S0": "rle", "S1": "rle", "S2": "dense", "S3": "dense", "A0": "rle",
+                                               "A1": "dense", "A2": "dense", "A3": "dense"}, 1.0, 400, (0.8, 0.7)),
+    ("rle_all_layers_constant", 22050, 512, True, {f"{k}{i}": "rle" for k in "SA" for i in range(4)}, 2.0, 300,
+     (1.0, 1.0)),
+    ("rle_all_layers_sticky", 44100, 441, True, {f"{k}{i}": "rle" for k in "SA" for i in range(4)}, 0.5, 350,
+     (0.95, 0.9)),
+    ("rle_single_frame", 22050, 512, True, None, 5.0, 1, (0.0, 0.0)),
+    ("dense_no_frames", 22050, 512, False, None, 5.0, 0, (0.0, 0.0)),
+]
+
+
+def sticky_stream(rng, n, vocab, stick):
+    """Token stream whose value repeats with probability `stick` (runs exercise the RLE duration bookkeeping)."""
+    out = np.empty(n, dtype=np.int64)
+    cur = int(rng.integers(vocab))
+    for i in range(n):
+        if i == 0 or rng.random() >= stick:
+            cur = int(rng.integers(vocab))
+        out[i] = cur
+    return out
+
+
+def ndjson_cases(nat) -> None:
+    """Known-answer NDJSON bodies from the reference's own StreamingProtocol.create_ndjson_stream (nat.py:4452)."""
+    cases = {}
+    for name, sr, hop, rle, enc, key_s, n, (stick_s, stick_a) in NDJSON_CASES:
+        rng = np.random.default_rng(sum(map(ord, name)))
+        sem = [sticky_stream(rng, n, 1024, stick_s) for _ in range(4)]
+        ac = [sticky_stream(rng, n, 1024, stick_a) for _ in range(4)]
+        proto = nat.StreamingProtocol(sample_rate=sr, hop_length=hop, rle_mode=rle, codebook_size=1024,
+                                      num_semantic_layers=4, num_acoustic_layers=4,
+                                      per_layer_encoding=None if enc is None else dict(enc),
+                                      keyframe_interval_seconds=key_s)
+        tokens = {"semantic_codes": [torch.from_numpy(s)[None] for s in sem],
+                  "acoustic_codes": [torch.from_numpy(a)[None] for a in ac]}
+        text = proto.create_ndjson_stream(tokens, metadata={"case": name}, processing_stats={"n": n},
+                                          duration_seconds=n * hop / sr)
+        lines = text.split("\n")
+        assert json.loads(lines[0])["event"] == "header" and json.loads(lines[-1])["event"] == "end"
+        cases[name] = {"sr": sr, "hop": hop, "rle": rle, "per_layer_encoding": enc, "keyframe_interval_seconds": key_s,
+                       "semantic": [s.tolist() for s in sem], "acoustic": [a.tolist() for a in ac],
+                       "header": lines[0], "body": lines[1:-1], "end": lines[-1]}
+    with open(os.path.join(GOLDEN, "ndjson_cases.json"), "w") as f:
+        json.dump(cases, f, separators=(",", ":"))
+    print("ndjson_cases:", {k: len(v["body"]) for k, v in cases.items()})
+
+
 def main() -> None:
     os.makedirs(GOLDEN, exist_ok=True)
     nat = load_reference()
     torch.set_num_threads(max(1, torch.get_num_threads()))
+    if "ndjson" in sys.argv[1:]:                              # `python -m oracle.make_golden ndjson`: only that file
+        ndjson_cases(nat)
+        return
     rvq_case(nat, "rvq_small", seed=7, D=64, K=128, L=4, B=1, T=50, store_codebooks=True)
     rvq_case(nat, "rvq_ragged", seed=11, D=80, K=300, L=3, B=2, T=37, store_codebooks=True)
     rvq_case(nat, "rvq_ties", seed=13, D=64, K=64, L=2, B=1, T=9, store_codebooks=True, duplicate_rows=True)
@@ -180,6 +235,7 @@ def main() -> None:
     spectral_case(nat, "spectral_noise_24000", noise, 24000)
     spectral_case(nat, "spectral_short", noise[:1000], 22050)         # shorter than n_fft: one zero-padded frame
     pipeline_case(nat, "pipeline_tone_argmin")
+    ndjson_cases(nat)
 
 
 if __name__ == "__main__":
