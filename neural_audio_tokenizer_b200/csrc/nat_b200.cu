@@ -344,7 +344,7 @@ static int launch_layer0_prep(const nat_rvq_codebooks* cb, const Workspace& ws, 
     } else {
         const size_t smem = static_cast<size_t>(rows::kPrepFrames) * (cb->dp + 1) * sizeof(float);
         if (smem <= 200 * 1024) {
-            NAT_LAUNCH(0, st, rows::prep_bct_fused_kernel<<<(n + rows::kPrepFrames - 1) / rows::kPrepFrames, 256, smem, st>>>(
+            NAT_LAUNCH(0, st, rows::prep_bct_fused_kernel<<<(n + rows::kPrepFrames - 1) / rows::kPrepFrames, rows::kPrepThreads, smem, st>>>(
                 x, T, cb->D, n0, n, cb->dp, ws.r, ws.a, ws.rowinfo, ws.rowamax, cb->lc));
         } else {
             dim3 grid((n + 31) / 32, cb->dp / 32);

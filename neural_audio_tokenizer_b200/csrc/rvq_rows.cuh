@@ -141,11 +141,13 @@ prep_rows_kernel(const float* __restrict__ x, long long x_ld, int n, int D, int 
 // (coalesced 128-byte reads along time), then each warp turns 4 frames into fp32 rows, fp16 operand rows and the
 // {alpha, bias, window} triple. One HBM read of x, one write of r and A. Dynamic smem: 32 * (dp + 1) floats.
 constexpr int kPrepFrames = 32;
-__global__ void __launch_bounds__(256)
+constexpr int kPrepThreads = 512;                       // 16 warps: 2 CTAs of 98 KB per SM keep 32 warps of loads in flight
+__global__ void __launch_bounds__(kPrepThreads)
 prep_bct_fused_kernel(const float* __restrict__ x, long long T, int D, long long n0, int n, int dp,
                       float* __restrict__ r, __half* __restrict__ a, float4* __restrict__ rowinfo,
                       float* __restrict__ rowamax, const LayerConst* __restrict__ lc) {
     extern __shared__ float s_tile[];                   // [32][dp + 1]
+    constexpr int kWarps = kPrepThreads / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ld = dp + 1;
     const int f0 = blockIdx.x * kPrepFrames;
@@ -155,20 +157,22 @@ prep_bct_fused_kernel(const float* __restrict__ x, long long T, int D, long long
         const long long g = n0 + f, b = g / T, t = g - b * T;
         src = b * D * T + t;
     }
-    // lane = frame (consecutive t: one 128-byte line per feature), warps stride over features, 8 loads in flight
-    for (int d0 = warp * 8; d0 < dp; d0 += 64) {
-        float v[8];
+    // lane = frame (consecutive t: one 128-byte line per feature), warps stride over features, 16 loads in flight
+    // per thread (the kernel is latency-bound otherwise: HBM needs ~30 KB in flight per SM)
+    constexpr int U = 16;
+    for (int d0 = warp * U; d0 < dp; d0 += kWarps * U) {
+        float v[U];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < U; ++u) {
             const int d = d0 + u;
-            v[u] = (src >= 0 && d < D) ? __ldg(x + src + static_cast<long long>(d) * T) : 0.f;
+            v[u] = (src >= 0 && d < D) ? __ldcs(x + src + static_cast<long long>(d) * T) : 0.f;
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
+        for (int u = 0; u < U; ++u)
             if (d0 + u < dp) s_tile[lane * ld + d0 + u] = v[u];
     }
     __syncthreads();
-    for (int fr = warp; fr < kPrepFrames; fr += 8) {
+    for (int fr = warp; fr < kPrepFrames; fr += kWarps) {
         const int row = f0 + fr;
         if (row >= n) break;                            // warp-uniform
         const float* src_row = s_tile + fr * ld;

@@ -128,3 +128,21 @@ def test_patch_reference_module_rebinds_names(nat):
         assert nat.T.MelSpectrogram is b200.MelSpectrogram and hasattr(nat.T, "Resample")
     finally:
         nat.ResidualVectorQuantizer, nat.T = saved
+
+
+@pytest.mark.parametrize("rle", [False, True])
+def test_native_ndjson_stream_equals_live_reference(nat, rle):
+    """The drop-in create_ndjson_stream, bound to a live reference StreamingProtocol, returns the reference's own
+    text (header and end events included) for the same token streams."""
+    from neural_audio_tokenizer_b200 import ndjson as nd
+    rng = np.random.default_rng(77)
+    n = 900
+    sem = [torch.from_numpy(np.repeat(rng.integers(0, 1024, n // 3), 3))[None] for _ in range(4)]
+    ac = [torch.from_numpy(rng.integers(0, 1024, n))[None] for _ in range(4)]
+    tokens = {"semantic_codes": sem, "acoustic_codes": ac}
+    kw = dict(sample_rate=22050, hop_length=512, rle_mode=rle, codebook_size=1024, keyframe_interval_seconds=2.0)
+    want = nat.StreamingProtocol(**kw).create_ndjson_stream(tokens, metadata={"k": 1}, processing_stats={"n": n},
+                                                            duration_seconds=n * 512 / 22050)
+    got = nd.create_ndjson_stream(nat.StreamingProtocol(**kw), tokens, metadata={"k": 1}, processing_stats={"n": n},
+                                  duration_seconds=n * 512 / 22050)
+    assert got == want
