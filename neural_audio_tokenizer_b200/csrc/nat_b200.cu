@@ -159,11 +159,13 @@ bool carve(void* base, size_t bytes, int dp, int L, long long want_rows, Workspa
 
 template <int NV>
 static cudaError_t stack_kernel_attrs() {
-    cudaError_t e = cudaFuncSetAttribute(nat::stack::rvq_stack_kernel<NV, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         nat::stack::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(nat::stack::rvq_stack_kernel<NV, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                nat::stack::SMEM_BYTES);
+    const void* fns[4] = {(const void*)nat::stack::rvq_stack_kernel<NV, 1, false>, (const void*)nat::stack::rvq_stack_kernel<NV, 2, false>,
+                          (const void*)nat::stack::rvq_stack_kernel<NV, 1, true>, (const void*)nat::stack::rvq_stack_kernel<NV, 2, true>};
+    for (const void* f : fns) {
+        cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, nat::stack::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 // One persistent launch of the fused stack kernel: plain grid (pair == 1) or clusters of two CTAs (pair == 2).
@@ -183,8 +185,13 @@ static cudaError_t launch_stack(int pair, int grid, cudaStream_t st, const CUten
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (pair == 2) return cudaLaunchKernelEx(&cfg, nat::stack::rvq_stack_kernel<NV, 2>, map_a, map_b, sa);
-    return cudaLaunchKernelEx(&cfg, nat::stack::rvq_stack_kernel<NV, 1>, map_a, map_b, sa);
+    // the instrumented instantiation runs only while counters or timing experiments are switched on
+    const bool dbg = sa.dbg != nullptr || sa.dbg_mode != 0;
+    if (pair == 2)
+        return dbg ? cudaLaunchKernelEx(&cfg, nat::stack::rvq_stack_kernel<NV, 2, true>, map_a, map_b, sa)
+                   : cudaLaunchKernelEx(&cfg, nat::stack::rvq_stack_kernel<NV, 2, false>, map_a, map_b, sa);
+    return dbg ? cudaLaunchKernelEx(&cfg, nat::stack::rvq_stack_kernel<NV, 1, true>, map_a, map_b, sa)
+               : cudaLaunchKernelEx(&cfg, nat::stack::rvq_stack_kernel<NV, 1, false>, map_a, map_b, sa);
 }
 
 struct nat_rvq_codebooks {

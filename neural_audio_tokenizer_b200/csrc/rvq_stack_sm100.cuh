@@ -105,12 +105,22 @@ struct StackArgs {
 enum { DBG_TMA_WAIT_READY = 0, DBG_TMA_WAIT_EMPTY, DBG_MMA_WAIT_TEMPTY, DBG_MMA_WAIT_FULL, DBG_EPI_WAIT_TFULL,
        DBG_EPI_WAIT_CEMPTY, DBG_EPI_TOTAL, DBG_UPD_WAIT_CFULL, DBG_UPD_TOTAL, DBG_KERNEL_TOTAL, DBG_EPI_WAIT_LD, DBG_EPI_EVENTS, DBG_UPD_DECIDE, DBG_UPD_RESID, DBG_UPD_FENCE, DBG_SLOTS = 16 };
 
-struct WaitClock {
+// Instrumentation exists only in the DBG instantiation of the kernel: the production build carries no counters,
+// no clock reads and no experiment switches (they cost registers in the 40-register roles).
+template <bool DBG>
+struct WaitClockT {
     long long acc = 0;
     bool on;
-    __device__ explicit WaitClock(bool enabled) : on(enabled) {}
+    __device__ explicit WaitClockT(bool enabled) : on(enabled) {}
     __device__ __forceinline__ long long begin() const { return on ? clock64() : 0; }
     __device__ __forceinline__ void end(long long t0) { if (on) acc += clock64() - t0; }
+};
+template <>
+struct WaitClockT<false> {
+    static constexpr long long acc = 0;
+    __device__ explicit WaitClockT(bool) {}
+    __device__ __forceinline__ long long begin() const { return 0; }
+    __device__ __forceinline__ void end(long long) {}
 };
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -199,13 +209,16 @@ __device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __ffma2_rn(b
 //   frames are all out of range). Cross-CTA protocol: both TMA producers signal the leader's `full` barrier, the
 //   leader's commits arrive on `empty` / `tfull` in both CTAs, both candidate warpgroups arrive on the leader's
 //   `tempty`.
-template <int NV, int PAIR>
+template <int NV, int PAIR, bool DBG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp], box 64 x 128, SWIZZLE_128B
                  const __grid_constant__ CUtensorMap map_b,   // fp16 [L*kp, dp], box 64 x (256 / PAIR), SWIZZLE_128B
                  const __grid_constant__ StackArgs p) {
     static_assert(PAIR == 1 || PAIR == 2, "one CTA or a CTA pair");
     using SM = Smem<PAIR>;
+    using WaitClock = WaitClockT<DBG>;
+    const int dbg_mode = DBG ? p.dbg_mode : 0;
+    unsigned long long* const dbg_out = DBG ? p.dbg : nullptr;
     constexpr int STAGES = SM::STAGES, B_BYTES = SM::B_BYTES;
     constexpr int OFF_A = SM::OFF_A, OFF_B = SM::OFF_B, OFF_LIST_S = SM::OFF_LIST_S, OFF_LIST_I = SM::OFF_LIST_I,
                   OFF_HAND = SM::OFF_HAND, OFF_CN = SM::OFF_CN, OFF_BARS = SM::OFF_BARS;
@@ -267,7 +280,7 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
         // ------------------------------------------------------------------ TMA producer (lane 0 issues)
         uint32_t s = 0, ph = 0;
         unsigned job = 0;
-        WaitClock w_ready(p.dbg != nullptr), w_empty(p.dbg != nullptr);
+        WaitClock w_ready(dbg_out != nullptr), w_empty(dbg_out != nullptr);
         const long long t_start = w_ready.begin();
         for (int g0 = 0; g0 < my_tiles; g0 += group) {
             const int gs = min(group, my_tiles - g0);
@@ -292,7 +305,7 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
                                 w_empty.end(t1);
                                 if (PAIR == 2) {
                                     // both CTAs' bytes are counted on the leader's barrier
-                                    const bool skip_a = (p.dbg_mode & 16) && chunk > 0;      // timing experiment only
+                                    const bool skip_a = (dbg_mode & 16) && chunk > 0;      // timing experiment only
                                     if (leader) mbar_arrive_expect_tx(&full[s], 2 * ((skip_a ? 0 : A_STAGE_BYTES) + B_BYTES));
                                     const uint32_t bar = mapa_rank(smem_u32(&full[s]), 0);
                                     if (!skip_a)
@@ -313,8 +326,8 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
                 }
             }
         }
-        if (p.dbg != nullptr && lane == 0) {
-            unsigned long long* d = p.dbg + static_cast<size_t>(blockIdx.x) * DBG_SLOTS;
+        if (dbg_out != nullptr && lane == 0) {
+            unsigned long long* d = dbg_out + static_cast<size_t>(blockIdx.x) * DBG_SLOTS;
             d[DBG_TMA_WAIT_READY] = w_ready.acc;
             d[DBG_TMA_WAIT_EMPTY] = w_empty.acc;
             d[DBG_KERNEL_TOTAL] = clock64() - t_start;
@@ -325,7 +338,7 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
             constexpr uint32_t idesc = umma_idesc_f16_f32(BLOCK_M * PAIR, BLOCK_N);
             uint32_t s = 0, ph = 0;
             const int total = p.L * my_tiles * n_chunks;
-            WaitClock w_tempty(p.dbg != nullptr), w_full(p.dbg != nullptr);
+            WaitClock w_tempty(dbg_out != nullptr), w_full(dbg_out != nullptr);
             for (int it = 0; it < total; ++it) {
                 const uint32_t as = it & 1, aph = (it >> 1) & 1;
                 const long long t0 = w_tempty.begin();
@@ -355,8 +368,8 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
-            if (p.dbg != nullptr) {
-                unsigned long long* d = p.dbg + static_cast<size_t>(blockIdx.x) * DBG_SLOTS;
+            if (dbg_out != nullptr) {
+                unsigned long long* d = dbg_out + static_cast<size_t>(blockIdx.x) * DBG_SLOTS;
                 d[DBG_MMA_WAIT_TEMPTY] = w_tempty.acc;
                 d[DBG_MMA_WAIT_FULL] = w_full.acc;
             }
@@ -378,8 +391,8 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
         const uint32_t cnbuf = smem_u32(smem + OFF_CN);
         sts_f32x2(cnbuf + tid * 8, __ldg(reinterpret_cast<const float2*>(p.cn32) + tid));
         uint32_t it = 0, job = 0;
-        WaitClock w_tfull(p.dbg != nullptr), w_cempty(p.dbg != nullptr), w_ld(p.dbg != nullptr);
-        unsigned long long n_events = 0;
+        WaitClock w_tfull(dbg_out != nullptr), w_cempty(dbg_out != nullptr), w_ld(dbg_out != nullptr);
+        [[maybe_unused]] unsigned long long n_events = 0;
         const long long t_epi = w_tfull.begin();
         for (int g0 = 0; g0 < my_tiles; g0 += group) {
             const int gs = min(group, my_tiles - g0);
@@ -457,7 +470,7 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
                                 if (!filter) {
                                     m = fminf(m, mn);
                                 } else if (mn <= thr) {
-                                    ++n_events;
+                                    if (DBG) ++n_events;
                                     m = fminf(m, mn);
                                     // m + W rounded up: the kept set must be a superset of the exact window
                                     thr = fmaf(fabsf(m) + window, 2.4e-7f, m + window);
@@ -483,7 +496,7 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
                             for (int g = 0; g < BLOCK_N / 32; ++g) {
                                 tmem_ld_32x32b_x32(taddr + g * 32, va);
                                 { const long long tw = w_ld.begin(); tmem_wait_ld(); w_ld.end(tw); }
-                                if ((p.dbg_mode & 15) < 6) scan32(va, g, false);
+                                if ((dbg_mode & 15) < 6) scan32(va, g, false);
                             }
                             if (valid) thr = fmaf(fabsf(m) + window, 2.4e-7f, m + window);
                         }
@@ -491,7 +504,7 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
                         for (int g = 0; g < BLOCK_N / 32; ++g) {
                             tmem_ld_32x32b_x32(taddr + g * 32, va);
                             { const long long tw = w_ld.begin(); tmem_wait_ld(); w_ld.end(tw); }
-                            if ((p.dbg_mode & 15) < 6) scan32(va, g, true);
+                            if ((dbg_mode & 15) < 6) scan32(va, g, true);
                         }
                         // accumulator stage drained: hand it back to the MMA warp
                         tcgen05_fence_before();
@@ -521,7 +534,7 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
                             ++n;
                         }
                     }
-                    if ((p.dbg_mode & 15) >= 6) { n = 1; sts_u16(hrec + 2, 0); overflow = false; }
+                    if ((dbg_mode & 15) >= 6) { n = 1; sts_u16(hrec + 2, 0); overflow = false; }
                     if (!valid) n = 0;
                     else if (overflow || n == 0 || n > HCAP) n = HAND_SCAN;
                     sts_u16(hrec, static_cast<unsigned short>(n));
@@ -530,8 +543,8 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
                 }
             }
         }
-        if (p.dbg != nullptr && warp == WARP_EPI0 && lane == 0) {
-            unsigned long long* d = p.dbg + static_cast<size_t>(blockIdx.x) * DBG_SLOTS;
+        if (dbg_out != nullptr && warp == WARP_EPI0 && lane == 0) {
+            unsigned long long* d = dbg_out + static_cast<size_t>(blockIdx.x) * DBG_SLOTS;
             d[DBG_EPI_WAIT_TFULL] = w_tfull.acc;
             d[DBG_EPI_WAIT_CEMPTY] = w_cempty.acc;
             d[DBG_EPI_TOTAL] = clock64() - t_epi;
@@ -549,7 +562,7 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
         const int uw = warp - WARP_UPD0;
         const int dp4 = p.dp >> 2;
         uint32_t job = 0;
-        WaitClock w_cfull(p.dbg != nullptr), w_res(p.dbg != nullptr), w_dec(p.dbg != nullptr), w_fence(p.dbg != nullptr);
+        WaitClock w_cfull(dbg_out != nullptr), w_res(dbg_out != nullptr), w_dec(dbg_out != nullptr), w_fence(dbg_out != nullptr);
         const long long t_upd = w_cfull.begin();
         for (int g0 = 0; g0 < my_tiles; g0 += group) {
             const int gs = min(group, my_tiles - g0);
@@ -583,7 +596,7 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
                     if (lane < ROWS_PER_UPD_WARP) rec = hand[slot * BLOCK_M + uw * ROWS_PER_UPD_WARP + lane];
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&cempty[slot]);
-                    if ((p.dbg_mode & 15) == 3 || (p.dbg_mode & 15) == 7) {
+                    if ((dbg_mode & 15) == 3 || (dbg_mode & 15) == 7) {
                         __syncwarp();
                         if (lane == 0) st_release(&ready[uw], job + 1);
                         continue;
@@ -769,8 +782,8 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
                 }
             }
         }
-        if (p.dbg != nullptr && uw == 0 && lane == 0) {
-            unsigned long long* d = p.dbg + static_cast<size_t>(blockIdx.x) * DBG_SLOTS;
+        if (dbg_out != nullptr && uw == 0 && lane == 0) {
+            unsigned long long* d = dbg_out + static_cast<size_t>(blockIdx.x) * DBG_SLOTS;
             d[DBG_UPD_WAIT_CFULL] = w_cfull.acc;
             d[DBG_UPD_TOTAL] = clock64() - t_upd;
             d[DBG_UPD_RESID] = w_res.acc;
