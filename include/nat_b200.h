@@ -101,6 +101,24 @@ int nat_rvq_encode_f32(const nat_rvq_codebooks* cb, const float* x_dev, int layo
                        float commitment_weight, unsigned long long* stats_dev,
                        void* workspace_dev, size_t workspace_bytes, int flags, void* stream);
 
+/* Sampling form of the same call: the reference's DEFAULT selection mode (nat.py:2150-2154, taken whenever
+ * `self.training or self.use_stochastic`): probs = softmax(-cdist / temperature); codes = multinomial(probs, 1), which
+ * ATen evaluates as argmax_k probs_k / q_k with q ~ Exp(1) per (frame, code). Every code is scored exactly (fp64
+ * accumulation); no tensor-core pass, so this path is for the reference's own clip sizes, not for bulk throughput.
+ *   temperatures_host  float [L] on the HOST; a layer with temperature <= 0 takes the exact argmin instead
+ *                      (per-layer `use_stochastic`, nat.py:2105)
+ *   noise_dev          float [L, B*T, K] on the device: the Exp(1) draws of each sampling layer in the order the
+ *                      reference makes them (one `empty_like(probs).exponential_(1)` per layer from torch's CPU
+ *                      generator) -- codes then equal the reference's except at near-ties of probs / q; or NULL:
+ *                      q comes from Philox4x32-10 keyed by philox_seed (counter: frame, code, philox_draw + layer),
+ *                      equal to the reference in distribution only
+ * Outputs as nat_rvq_encode_f32. */
+int nat_rvq_sample_f32(const nat_rvq_codebooks* cb, const float* x_dev, int layout, int64_t B, int64_t T,
+                       void* codes_out_dev, int code_dtype, float* quantized_out_dev, float* loss_out_dev,
+                       float commitment_weight, const float* temperatures_host, const float* noise_dev,
+                       unsigned long long philox_seed, unsigned long long philox_draw,
+                       void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* Same call, timed: CUDA events around every kernel launch on `stream`, then a stream synchronise, and the summed
  * device milliseconds per kernel class in prof_ms_host[NAT_PROF_FIELDS] (bench.py's roofline leg; not a hot path). */
 #define NAT_PROF_FIELDS 8

@@ -383,6 +383,10 @@ struct EncodeCall {
     const nat_rvq_codebooks* cb;
     const float* x; int layout; long long T, N;
     void* codes; int code_dtype; float* quantized; bool want_loss; unsigned long long* stats; bool exact;
+    // sampling mode (nat_rvq_sample_f32): per-layer temperatures (<= 0: that layer takes the exact argmin), optional
+    // host-drawn noise [L, N, K], Philox key / draw base otherwise
+    const float* temperatures = nullptr; const float* noise = nullptr;
+    unsigned long long seed = 0, draw_base = 0;
 };
 
 static int encode_chunk(const EncodeCall& c, const Workspace& ws, const CUtensorMap& map_a, long long n0, int n,
@@ -394,7 +398,7 @@ static int encode_chunk(const EncodeCall& c, const Workspace& ws, const CUtensor
     if (int rc = launch_layer0_prep(cb, ws, c.x, c.layout, c.T, n0, n, st)) return rc;
     NAT_CUDA(cudaMemsetAsync(ws.scan_count, 0, sizeof(int) * cb->L, st));
     const int n_tiles = (n + gemm::BLOCK_M - 1) / gemm::BLOCK_M;
-    if (!c.exact && fused_enabled() && cb->dp <= 1024) {
+    if (!c.exact && c.temperatures == nullptr && fused_enabled() && cb->dp <= 1024) {
         // one persistent launch for all L layers (rvq_stack_sm100.cuh)
         stack::StackArgs sa;
         sa.cbf = cb->cbf; sa.cn64 = cb->cn64; sa.cn32 = cb->cn32; sa.lc = cb->lc;
@@ -440,7 +444,16 @@ static int encode_chunk(const EncodeCall& c, const Workspace& ws, const CUtensor
         ua.n = n; ua.K = cb->K; ua.dp = cb->dp; ua.code_dtype = c.code_dtype;
         const int scan_grid = cb->sm_count * 4;
         const size_t scan_smem = static_cast<size_t>(cb->dp) * sizeof(float);
-        if (!c.exact) {
+        if (c.temperatures != nullptr && c.temperatures[l] > 0.f) {
+            rows::SampleArgs sargs;
+            sargs.noise = c.noise != nullptr ? c.noise + (static_cast<long long>(l) * c.N + n0) * cb->K : nullptr;
+            sargs.seed = c.seed;
+            sargs.row0 = static_cast<unsigned long long>(n0);
+            sargs.draw = static_cast<unsigned>(c.draw_base + l);
+            sargs.temperature = c.temperatures[l];
+            const size_t smem = scan_smem + static_cast<size_t>(cb->K) * sizeof(float);
+            NAT_LAUNCH(3, st, rows::sample_scan_kernel<<<std::min(n, scan_grid), rows::kScanThreads, smem, st>>>(ua, sargs));
+        } else if (!c.exact && c.temperatures == nullptr) {
             NAT_LAUNCH(1, st, gemm::rvq_gemm_topk_kernel<false><<<std::min(n_tiles, cb->sm_count), gemm::NUM_THREADS,
                                                                    gemm::SMEM_BYTES, st>>>(
                 map_a, cb->map_b, n, n_tiles, cb->kp / gemm::BLOCK_N, cb->dp / gemm::BLOCK_K, l * cb->kp, ws.rowinfo,
@@ -485,10 +498,11 @@ static bool overlap_enabled() {
     return on;
 }
 
-int nat_rvq_encode_f32(const nat_rvq_codebooks* cb_const, const float* x_dev, int layout, int64_t B, int64_t T,
+static int encode_impl(const nat_rvq_codebooks* cb_const, const float* x_dev, int layout, int64_t B, int64_t T,
                        void* codes_out_dev, int code_dtype, float* quantized_out_dev, float* loss_out_dev,
                        float commitment_weight, unsigned long long* stats_dev, void* workspace_dev,
-                       size_t workspace_bytes, int flags, void* stream) {
+                       size_t workspace_bytes, int flags, void* stream, const float* temperatures,
+                       const float* noise_dev, unsigned long long seed, unsigned long long draw_base) {
     using namespace nat;
     nat_rvq_codebooks* cb = const_cast<nat_rvq_codebooks*>(cb_const);
     if (cb == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null codebook handle");
@@ -535,6 +549,7 @@ int nat_rvq_encode_f32(const nat_rvq_codebooks* cb_const, const float* x_dev, in
 
     EncodeCall call{cb, x_dev, layout, T, N, codes_out_dev, code_dtype, quantized_out_dev, loss_out_dev != nullptr,
                     stats_dev, (flags & NAT_RVQ_EXACT_SCAN) != 0};
+    call.temperatures = temperatures; call.noise = noise_dev; call.seed = seed; call.draw_base = draw_base;
     for (int i = 0; i < n_lanes; ++i) {
         NAT_CUDA(cudaMemsetAsync(ws[i].loss_acc, 0, sizeof(double) * cb->L, lane_st[i]));
         if (cb->dp != cb->D) NAT_CUDA(cudaMemsetAsync(ws[i].a, 0, static_cast<size_t>(ws[i].rows) * cb->dp * 2, lane_st[i]));
@@ -558,6 +573,33 @@ int nat_rvq_encode_f32(const nat_rvq_codebooks* cb_const, const float* x_dev, in
         NAT_CUDA(cudaGetLastError());
     }
     return NAT_OK;
+}
+
+int nat_rvq_encode_f32(const nat_rvq_codebooks* cb, const float* x_dev, int layout, int64_t B, int64_t T,
+                       void* codes_out_dev, int code_dtype, float* quantized_out_dev, float* loss_out_dev,
+                       float commitment_weight, unsigned long long* stats_dev, void* workspace_dev,
+                       size_t workspace_bytes, int flags, void* stream) {
+    return encode_impl(cb, x_dev, layout, B, T, codes_out_dev, code_dtype, quantized_out_dev, loss_out_dev,
+                       commitment_weight, stats_dev, workspace_dev, workspace_bytes, flags, stream, nullptr, nullptr, 0, 0);
+}
+
+int nat_rvq_sample_f32(const nat_rvq_codebooks* cb, const float* x_dev, int layout, int64_t B, int64_t T,
+                       void* codes_out_dev, int code_dtype, float* quantized_out_dev, float* loss_out_dev,
+                       float commitment_weight, const float* temperatures_host, const float* noise_dev,
+                       unsigned long long philox_seed, unsigned long long philox_draw, void* workspace_dev,
+                       size_t workspace_bytes, void* stream) {
+    if (cb == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null codebook handle");
+    if (temperatures_host == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null temperature array");
+    for (int l = 0; l < cb->L; ++l)
+        if (!(temperatures_host[l] == temperatures_host[l]))
+            return fail(NAT_ERR_INVALID_ARGUMENT, "temperature of layer %d is NaN", l);
+    const size_t smem = static_cast<size_t>(cb->dp) * 4 + static_cast<size_t>(cb->K) * 4;
+    if (smem > 200 * 1024)
+        return fail(NAT_ERR_UNSUPPORTED, "sampling mode keeps K scores in shared memory: codebook_size %d is too large", cb->K);
+    NAT_CUDA(cudaFuncSetAttribute(nat::rows::sample_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    return encode_impl(cb, x_dev, layout, B, T, codes_out_dev, code_dtype, quantized_out_dev, loss_out_dev,
+                       commitment_weight, nullptr, workspace_dev, workspace_bytes, NAT_RVQ_SINGLE_STREAM, stream,
+                       temperatures_host, noise_dev, philox_seed, philox_draw);
 }
 
 int nat_rvq_encode_profile_f32(const nat_rvq_codebooks* cb, const float* x_dev, int layout, int64_t B, int64_t T,

@@ -451,6 +451,162 @@ full_scan_kernel(UpdateArgs p, const int* __restrict__ scan_list, const int* __r
     }
 }
 
+// ---------------------------------------------------------------------------------------------------- sampling
+// The reference's default selection (nat.py:2150-2154): probs = softmax(-cdist / temperature), then
+// torch.multinomial(probs, 1), which ATen evaluates as  argmax_k probs_k / q_k  with q ~ Exp(1) drawn for every
+// (frame, code) pair (aten/src/ATen/native/Distributions.cpp, multinomial, the n_sample == 1 path).
+//
+// One CTA per frame, every code scored exactly: d_k = sqrt(max(0, ||r||^2 - 2 r.c_k + ||c_k||^2)) from fp64
+// accumulation rounded to fp32 (the reference's fp32 sgemm expansion carries its own rounding), then the
+// same fp32 steps as ATen: z = -d / T, e = exp(z - max z), p = e / sum e, v = p / q, first maximum.
+//   noise != nullptr: q is read from noise[row * K + k] -- the host drew it from torch's CPU generator in the
+//     reference's order, so codes equal the reference's except where v's two best values nearly tie;
+//   noise == nullptr: q = -log(u), u in (0, 1] from Philox4x32-10 keyed by `seed`, counter (global row, k / 4, draw),
+//     a different random stream from torch's: equal in distribution only.
+struct SampleArgs {
+    const float* noise;            // [n, K] for this chunk and layer, or nullptr
+    unsigned long long seed;       // Philox key
+    unsigned long long row0;       // global index of the chunk's first frame (Philox counter)
+    unsigned draw;                 // distinguishes layers / calls in the Philox counter
+    float temperature;
+};
+
+__device__ __forceinline__ void philox4x32_10(uint32_t (&ctr)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int round = 0; round < 10; ++round) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr[0]), lo0 = 0xD2511F53u * ctr[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr[2]), lo1 = 0xCD9E8D57u * ctr[2];
+        const uint32_t n0 = hi1 ^ ctr[1] ^ k0, n2 = hi0 ^ ctr[3] ^ k1;
+        ctr[0] = n0; ctr[1] = lo1; ctr[2] = n2; ctr[3] = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+// Exp(1) from 32 random bits: u = (bits + 1) / 2^32 in (0, 1], q = -log(u) >= 0; q == 0 only for u == 1, replaced by
+// the smallest positive value the formula can produce so that p / q stays finite.
+__device__ __forceinline__ float exp1_from_bits(uint32_t bits) {
+    const float u = (static_cast<float>(bits >> 8) + 1.0f) * (1.0f / 16777216.0f);
+    const float q = -logf(u);
+    return q > 0.f ? q : 5.9604645e-8f;
+}
+
+template <int BLOCK>
+__device__ __forceinline__ float block_reduce_max(float v, float* sh) {
+    v = warp_max(v);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = sh[0];
+    for (int w = 1; w < BLOCK / 32; ++w) r = fmaxf(r, sh[w]);
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+sample_scan_kernel(UpdateArgs p, SampleArgs sa) {
+    extern __shared__ float4 s_dyn[];                   // [dp / 4] frame, then [K] scores
+    __shared__ float s_red[kScanWarps];
+    __shared__ double s_redd[kScanWarps];
+    __shared__ float s_bv[kScanWarps];
+    __shared__ int s_bi[kScanWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int dp4 = p.dp >> 2;
+    float4* s_row = s_dyn;
+    float* s_z = reinterpret_cast<float*>(s_dyn + dp4);
+    for (int row = blockIdx.x; row < p.n; row += gridDim.x) {
+        const float4* r4 = reinterpret_cast<const float4*>(p.r + static_cast<long long>(row) * p.dp);
+        double xn = 0.0;
+        for (int i = threadIdx.x; i < dp4; i += kScanThreads) {
+            const float4 v = r4[i];
+            s_row[i] = v;
+            xn += static_cast<double>(v.x) * v.x + static_cast<double>(v.y) * v.y + static_cast<double>(v.z) * v.z +
+                  static_cast<double>(v.w) * v.w;
+        }
+        xn = warp_sum(xn);
+        if (lane == 0) s_redd[warp] = xn;
+        __syncthreads();
+        xn = 0.0;
+        for (int w = 0; w < kScanWarps; ++w) xn += s_redd[w];
+        // z_k = -d_k / T for every code
+        for (int k0 = warp * kScanCodes; k0 < p.K; k0 += kScanWarps * kScanCodes) {
+            double acc[kScanCodes];
+            const float4* c4[kScanCodes];
+#pragma unroll
+            for (int c = 0; c < kScanCodes; ++c) {
+                acc[c] = 0.0;
+                c4[c] = reinterpret_cast<const float4*>(p.cb + static_cast<long long>(min(k0 + c, p.K - 1)) * p.dp);
+            }
+            for (int i = lane; i < dp4; i += 32) {
+                const float4 a = s_row[i];
+#pragma unroll
+                for (int c = 0; c < kScanCodes; ++c) {
+                    const float4 b = __ldg(c4[c] + i);
+                    acc[c] = fma(static_cast<double>(a.x), static_cast<double>(b.x), acc[c]);
+                    acc[c] = fma(static_cast<double>(a.y), static_cast<double>(b.y), acc[c]);
+                    acc[c] = fma(static_cast<double>(a.z), static_cast<double>(b.z), acc[c]);
+                    acc[c] = fma(static_cast<double>(a.w), static_cast<double>(b.w), acc[c]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < kScanCodes; ++c) {
+                const int k = k0 + c;
+                const double dot = warp_sum(acc[c]);
+                if (k < p.K && lane == 0) {
+                    const float d2 = static_cast<float>(fmax(xn + p.cn64[k] - 2.0 * dot, 0.0));
+                    s_z[k] = __fdiv_rn(-__fsqrt_rn(d2), sa.temperature);
+                }
+            }
+        }
+        __syncthreads();
+        float zmax = -__int_as_float(0x7F800000);
+        for (int k = threadIdx.x; k < p.K; k += kScanThreads) zmax = fmaxf(zmax, s_z[k]);
+        zmax = block_reduce_max<kScanThreads>(zmax, s_red);
+        float esum = 0.f;
+        for (int k = threadIdx.x; k < p.K; k += kScanThreads) {
+            const float e = expf(s_z[k] - zmax);
+            s_z[k] = e;
+            esum += e;
+        }
+        esum = warp_sum(esum);
+        if (lane == 0) s_red[warp] = esum;
+        __syncthreads();
+        esum = 0.f;
+        for (int w = 0; w < kScanWarps; ++w) esum += s_red[w];
+        // v_k = (e_k / sum) / q_k, first maximum
+        float bv = -1.f;
+        int bi = 0x7FFFFFFF;
+        for (int k = threadIdx.x; k < p.K; k += kScanThreads) {
+            float q;
+            if (sa.noise != nullptr) {
+                q = __ldg(sa.noise + static_cast<long long>(row) * p.K + k);
+            } else {
+                const unsigned long long g = sa.row0 + static_cast<unsigned long long>(row);
+                uint32_t ctr[4] = {static_cast<uint32_t>(g), static_cast<uint32_t>(g >> 32), static_cast<uint32_t>(k >> 2), sa.draw};
+                philox4x32_10(ctr, static_cast<uint32_t>(sa.seed), static_cast<uint32_t>(sa.seed >> 32));
+                q = exp1_from_bits(ctr[k & 3]);
+            }
+            const float v = __fdiv_rn(__fdiv_rn(s_z[k], esum), q);
+            if (v > bv) { bv = v; bi = k; }              // k ascending per thread: first maximum kept
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { s_bv[warp] = bv; s_bi[warp] = bi; }
+        __syncthreads();
+        if (warp == 0) {
+            float b = s_bv[0];
+            int bj = s_bi[0];
+            for (int w = 1; w < kScanWarps; ++w)
+                if (s_bv[w] > b || (s_bv[w] == b && s_bi[w] < bj)) { b = s_bv[w]; bj = s_bi[w]; }
+            bj = min(max(bj, 0), p.K - 1);               // all-NaN rows (non-finite input) still yield a valid index
+            apply_code(p, row, bj);
+        }
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------- loss
 // Deterministic fixed-order sum of row_loss[0..n) added to *acc (one block).
 __global__ void __launch_bounds__(1024)

@@ -6,10 +6,16 @@ Mirrors the reference's Python surface for this path (nat.py = /root/reference/n
   * `VectorQuantizer.forward/decode/_update_ema`          nat.py:2119-2221
   * ValueError conditions for bad rank / channel count    nat.py:1378-1391, 2126-2138
 
-Contract: the native path implements the ARGMIN branch (nat.py:2155-2157). When a layer is in training mode or has
-`use_stochastic=True` the reference samples (nat.py:2150-2154); this module then calls `stochastic_delegate` if one
-was supplied and otherwise raises -- it never returns argmin codes when sampling was asked for.
-There is no CPU path: tensors must live on a CUDA device.
+Contract: the tensor-core path implements the ARGMIN branch (nat.py:2155-2157). When a layer has
+`use_stochastic=True` in eval mode the reference samples (nat.py:2150-2154, its default); this module then follows
+`sampling_mode`:
+  * "host_noise" (default): the Exp(1) draws behind `torch.multinomial(probs, 1)` are made on the host from torch's CPU
+    generator, in the reference's order, and shipped to the device (nat_rvq_sample_f32) -- seeded runs reproduce the
+    reference's codes except at near-ties of probs / q. Meant for the reference's own clip sizes (N*K floats per layer);
+  * "philox": device-side noise, equal to the reference in distribution only (stated, never silent);
+  * "delegate": call `stochastic_delegate` (e.g. the unmodified reference module).
+Training mode (EMA codebook updates, nat.py:2179-2181) always goes to `stochastic_delegate` or raises. The module
+never returns argmin codes when sampling was asked for. There is no CPU path: tensors must live on a CUDA device.
 """
 from __future__ import annotations
 
@@ -119,6 +125,61 @@ def _native_encode(pack: _CodebookPack, codebooks: Sequence[torch.Tensor], x_bct
     return codes, quantized, loss
 
 
+MAX_HOST_NOISE_BYTES = 1 << 30
+
+
+def _native_sample(pack: _CodebookPack, codebooks: Sequence[torch.Tensor], x_bct: torch.Tensor,
+                   commitment_weight: float, want_quantized: bool, want_loss: bool, temperatures: Sequence[float],
+                   mode: str, philox_draw: int = 0, code_dtype: torch.dtype = torch.int64):
+    """Sampling form of _native_encode. temperatures[l] <= 0 marks an argmin layer. Returns the same triple."""
+    lib = _lib.load()
+    _require_cuda(x_bct, "input")
+    if x_bct.dtype != torch.float32:
+        raise TypeError(f"expected float32 features, got {x_bct.dtype}")
+    dev = x_bct.device
+    x = x_bct if x_bct.is_contiguous() else x_bct.contiguous()
+    B, C, T = x.shape
+    L, K = len(codebooks), codebooks[0].shape[0]
+    N = B * T
+    dt = {torch.int64: _lib.CODES_I64, torch.int32: _lib.CODES_I32, torch.int16: _lib.CODES_I16}[code_dtype]
+    codes = torch.empty((L, B, T), dtype=code_dtype, device=dev)
+    quantized = torch.empty_like(x) if want_quantized else None
+    loss = torch.empty(L, dtype=torch.float32, device=dev) if want_loss else None
+    noise = None
+    if mode == "host_noise":
+        n_sampling = sum(1 for t in temperatures if t > 0)
+        if N * K * 4 * n_sampling > MAX_HOST_NOISE_BYTES:
+            raise RuntimeError(
+                f"sampling_mode='host_noise' would ship {N * K * 4 * n_sampling / 2**30:.1f} GiB of host-drawn noise "
+                f"({N} frames x {K} codes x {n_sampling} layers); use sampling_mode='philox' (distributional parity) "
+                "or use_stochastic=False")
+        # one draw per sampling layer, in layer order, exactly as torch.multinomial makes it on the CPU
+        # (`at::empty_like(probs).exponential_(1)`); argmin layers consume nothing
+        host = torch.zeros((L, N, K), dtype=torch.float32, pin_memory=N * K > 0)
+        for l, t in enumerate(temperatures):
+            if t > 0:
+                host[l].copy_(torch.empty((N, K), dtype=torch.float32).exponential_(1))
+        noise = host.to(dev, non_blocking=True)
+    elif mode != "philox":
+        raise ValueError(f"unknown sampling_mode {mode!r}")
+    if N == 0:
+        if loss is not None:
+            loss.fill_(float("nan"))
+        return codes, quantized, loss
+    temps = (ctypes.c_float * L)(*[float(t) for t in temperatures])
+    with torch.cuda.device(dev):
+        handle = pack.get(codebooks)
+        ws_bytes = lib.nat_rvq_workspace_bytes(handle, N)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.nat_rvq_sample_f32(
+            handle, x.data_ptr(), _lib.LAYOUT_BCT, B, T, codes.data_ptr(), dt,
+            quantized.data_ptr() if quantized is not None else None,
+            loss.data_ptr() if loss is not None else None, float(commitment_weight), temps,
+            noise.data_ptr() if noise is not None else None, int(torch.initial_seed()) & (2 ** 64 - 1),
+            int(philox_draw), ws.data_ptr(), ws_bytes, torch.cuda.current_stream(dev).cuda_stream))
+    return codes, quantized, loss
+
+
 def _native_decode(pack: _CodebookPack, codebooks: Sequence[torch.Tensor], codes: torch.Tensor, n_lists: int,
                    B: int, T: int) -> torch.Tensor:
     """codes [n_lists, B*T] int64 CUDA -> [B, D, T] fp32 (sum of per-layer gathers, nat.py:1438-1444)."""
@@ -154,8 +215,10 @@ class VectorQuantizer(nn.Module):
         self.register_buffer("ema_count", torch.zeros(codebook_size))
         self.register_buffer("ema_weight", self.codebook.clone())
         self.stochastic_delegate = None
+        self.sampling_mode = "host_noise"     # "host_noise" | "philox" | "delegate" (module docstring)
         self.exact_scan = False
         self._pack = _CodebookPack()
+        self._draws = 0
 
     def _argmin_mode(self) -> bool:
         return not (self.training or self.use_stochastic)
@@ -170,14 +233,19 @@ class VectorQuantizer(nn.Module):
         if C != self.input_dim:
             raise ValueError(f"Expected {self.input_dim} feature dimensions, got {C}")
         if not self._argmin_mode():
-            if self.stochastic_delegate is not None:
-                return self.stochastic_delegate(x if len(original_shape) == 3 else x.squeeze(0))
-            raise NotImplementedError(
-                "VectorQuantizer is in sampling mode (training=%s, use_stochastic=%s); the B200 path implements the "
-                "argmin branch of nat.py:2155-2157 only. Set use_stochastic=False and call eval(), or supply "
-                "`stochastic_delegate`." % (self.training, self.use_stochastic))
-        codes, quantized, loss = _native_encode(self._pack, [self.codebook], x, self.commitment_weight, True, True,
-                                                exact_scan=self.exact_scan)
+            if self.training or self.sampling_mode == "delegate":
+                if self.stochastic_delegate is not None:
+                    return self.stochastic_delegate(x if len(original_shape) == 3 else x.squeeze(0))
+                raise NotImplementedError(
+                    "VectorQuantizer: training=%s, sampling_mode=%r: training (EMA updates, nat.py:2179-2181) and "
+                    "delegated sampling need `stochastic_delegate`; eval-mode sampling runs natively with "
+                    "sampling_mode 'host_noise' or 'philox'." % (self.training, self.sampling_mode))
+            codes, quantized, loss = _native_sample(self._pack, [self.codebook], x, self.commitment_weight, True, True,
+                                                    [self.temperature], self.sampling_mode, self._draws)
+            self._draws += 1
+        else:
+            codes, quantized, loss = _native_encode(self._pack, [self.codebook], x, self.commitment_weight, True, True,
+                                                    exact_scan=self.exact_scan)
         codes = codes[0]
         loss = loss[0]
         if len(original_shape) == 2:
@@ -221,7 +289,9 @@ class ResidualVectorQuantizer(nn.Module):
                             use_stochastic=use_stochastic)
             for _ in range(num_quantizers)
         ])
-        self.stochastic_delegate = None      # e.g. the reference module itself, for the sampling modes
+        self.stochastic_delegate = None      # e.g. the reference module itself (training, or sampling_mode "delegate")
+        self.sampling_mode = "host_noise"    # how eval-mode sampling layers get their noise (module docstring)
+        self._draws = 0
         self.codes_on_cpu = False            # one bulk D2H instead of per-element reads in the NDJSON emitter
         self.exact_scan = False              # debugging aid: exact fp64 full scan for every frame
         self.collect_stats = False
@@ -235,6 +305,16 @@ class ResidualVectorQuantizer(nn.Module):
     def _argmin_mode(self) -> bool:
         return all(q._argmin_mode() if isinstance(q, VectorQuantizer) else not (q.training or q.use_stochastic)
                    for q in self.quantizers)
+
+    def _needs_delegate(self) -> bool:
+        return self.sampling_mode == "delegate" or any(q.training for q in self.quantizers)
+
+    def _sample(self, x, want_quantized: bool, want_loss: bool):
+        temps = [float(q.temperature) if q.use_stochastic else 0.0 for q in self.quantizers]
+        out = _native_sample(self._pack, self._codebooks(), x, self.commitment_weight, want_quantized, want_loss,
+                             temps, self.sampling_mode, self._draws)
+        self._draws += len(self.quantizers)
+        return out
 
     def _validate(self, x):
         if x.dim() not in [2, 3]:
@@ -265,17 +345,20 @@ class ResidualVectorQuantizer(nn.Module):
         try:
             x = self._validate(x)
             if not self._argmin_mode():
-                if self.stochastic_delegate is not None:
-                    return self.stochastic_delegate(x)
-                raise NotImplementedError(
-                    "ResidualVectorQuantizer is in sampling mode (a layer has training=True or use_stochastic=True); "
-                    "the B200 path implements the argmin contract (nat.py:2155-2157). Use "
-                    "neural_audio_tokenizer_b200.install(tokenizer, force_argmin=True), or set "
-                    "`stochastic_delegate` to the reference module.")
-            stats = self._stats_tensor(x.device)
-            codes, quantized, loss = _native_encode(self._pack, self._codebooks(), x, self.commitment_weight, True,
-                                                    True, exact_scan=self.exact_scan, stats=stats)
-            self.last_stats = stats
+                if self._needs_delegate():
+                    if self.stochastic_delegate is not None:
+                        return self.stochastic_delegate(x)
+                    raise NotImplementedError(
+                        "ResidualVectorQuantizer: a layer is in training mode or sampling_mode is 'delegate', and no "
+                        "`stochastic_delegate` (the reference module) was supplied. Eval-mode sampling runs natively "
+                        "with sampling_mode 'host_noise' or 'philox'; install(tokenizer, force_argmin=True) gives the "
+                        "argmin contract (nat.py:2155-2157).")
+                codes, quantized, loss = self._sample(x, True, True)
+            else:
+                stats = self._stats_tensor(x.device)
+                codes, quantized, loss = _native_encode(self._pack, self._codebooks(), x, self.commitment_weight, True,
+                                                        True, exact_scan=self.exact_scan, stats=stats)
+                self.last_stats = stats
             total = loss[0]
             for l in range(1, loss.shape[0]):                # total_loss += loss, layer by layer (nat.py:1402)
                 total = total + loss[l]
@@ -293,9 +376,14 @@ class ResidualVectorQuantizer(nn.Module):
             try:
                 x = self._validate(x)
                 if not self._argmin_mode():
-                    if self.stochastic_delegate is not None:
-                        return self.stochastic_delegate.encode(x)
-                    raise NotImplementedError("encode(): a layer has use_stochastic=True; see forward()")
+                    if self._needs_delegate():
+                        if self.stochastic_delegate is not None:
+                            return self.stochastic_delegate.encode(x)
+                        raise NotImplementedError("encode(): sampling_mode is 'delegate' without a delegate; see forward()")
+                    # the reference's encode() runs the whole forward and drops the rest (nat.py:1422-1426); the losses
+                    # and the quantised sum draw nothing from the generator, so skipping them keeps the RNG stream
+                    codes, _, _ = self._sample(x, False, False)
+                    return self._finish_codes(codes)
                 stats = self._stats_tensor(x.device)
                 codes, _, _ = _native_encode(self._pack, self._codebooks(), x, self.commitment_weight, False, False,
                                              exact_scan=self.exact_scan, stats=stats)

@@ -155,6 +155,27 @@ def pipeline_case(nat, name: str):
     print(f"{name}: {len(frames)} frames, first S={frames[0]['S']} A={frames[0]['A']}")
 
 
+def rvq_sampling_case(nat, name: str, seed: int, D: int, K: int, L: int, T: int, noise_seed: int,
+                      argmin_layers=()) -> None:
+    """The reference in its DEFAULT mode (eval, use_stochastic=True, nat.py:2150-2154) with a seeded global generator:
+    the known answer for the sampling path. `argmin_layers` switches individual layers to use_stochastic=False."""
+    torch.manual_seed(seed)
+    rvq = nat.ResidualVectorQuantizer(D, K, L).eval()
+    for i in argmin_layers:
+        rvq.quantizers[i].use_stochastic = False
+    x = torch.randn(1, D, T, generator=torch.Generator().manual_seed(1234))
+    torch.manual_seed(noise_seed)
+    with torch.no_grad():
+        quantized, codes, losses = rvq(x)
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"),
+                        x=x.numpy(), codebooks=np.stack([q.codebook.numpy() for q in rvq.quantizers]),
+                        codes=np.stack([c.numpy() for c in codes]), quantized=quantized.numpy(),
+                        vq_loss=np.float32(losses["vq_loss"]), noise_seed=np.int64(noise_seed),
+                        temperatures=np.array([q.temperature if q.use_stochastic else 0.0 for q in rvq.quantizers],
+                                              dtype=np.float32))
+    print(name, "codes[:, 0, :6] =", np.stack([c.numpy() for c in codes])[:, 0, :6].tolist())
+
+
 NDJSON_CASES = [
     # name, sr, hop, rle, per_layer_encoding, keyframe interval, frames, stickiness of (semantic, acoustic) streams
     ("dense_22050", 22050, 512, False, None, 5.0, 200, (0.0, 0.0)),
@@ -207,12 +228,21 @@ def ndjson_cases(nat) -> None:
     print("ndjson_cases:", {k: len(v["body"]) for k, v in cases.items()})
 
 
+def sampling_cases(nat) -> None:
+    rvq_sampling_case(nat, "rvq_sampling_small", seed=7, D=64, K=128, L=4, T=300, noise_seed=99)
+    rvq_sampling_case(nat, "rvq_sampling_mixed", seed=8, D=48, K=100, L=4, T=120, noise_seed=5, argmin_layers=(1, 3))
+    rvq_sampling_case(nat, "rvq_sampling_wide", seed=9, D=200, K=300, L=2, T=64, noise_seed=6)
+
+
 def main() -> None:
     os.makedirs(GOLDEN, exist_ok=True)
     nat = load_reference()
     torch.set_num_threads(max(1, torch.get_num_threads()))
     if "ndjson" in sys.argv[1:]:                              # `python -m oracle.make_golden ndjson`: only that file
         ndjson_cases(nat)
+        return
+    if "sampling" in sys.argv[1:]:
+        sampling_cases(nat)
         return
     rvq_case(nat, "rvq_small", seed=7, D=64, K=128, L=4, B=1, T=50, store_codebooks=True)
     rvq_case(nat, "rvq_ragged", seed=11, D=80, K=300, L=3, B=2, T=37, store_codebooks=True)
@@ -236,6 +266,7 @@ def main() -> None:
     spectral_case(nat, "spectral_short", noise[:1000], 22050)         # shorter than n_fft: one zero-padded frame
     pipeline_case(nat, "pipeline_tone_argmin")
     ndjson_cases(nat)
+    sampling_cases(nat)
 
 
 if __name__ == "__main__":

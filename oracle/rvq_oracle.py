@@ -1,4 +1,4 @@
-"""Oracle for the residual vector quantiser (argmin contract).
+"""Oracle for the residual vector quantiser (argmin contract, and the sampling mode at the end of the file).
 
 TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
 
@@ -141,3 +141,85 @@ def exact_argmin_f64(rows: np.ndarray, codebook: np.ndarray) -> np.ndarray:
     c = codebook.astype(np.float64)
     d2 = (r * r).sum(1)[:, None] - 2.0 * r @ c.T + (c * c).sum(1)[None, :]
     return np.argmin(d2, axis=1)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Sampling mode (the reference's default selection, nat.py:2150-2154)
+# ----------------------------------------------------------------------------------------------------------------
+
+SAMPLING_NEAR_TIE_REL_GAP = 1e-4
+
+
+def vq_layer_sampling(x_bct: torch.Tensor, codebook: torch.Tensor, temperature: float, commitment_weight: float = 0.25,
+                      generator: torch.Generator = None):
+    """One VQ layer with `use_stochastic=True` in eval mode. `torch.multinomial(probs, 1)` (nat.py:2154) is spelled
+    out as ATen evaluates it on CPU -- q = empty_like(probs).exponential_(1); argmax(probs / q) -- so that the draw the
+    device path has to reproduce is explicit; tests/golden/rvq_sampling_*.npz (minted from the reference's own
+    multinomial call) pin that the spelling is bit-identical. Also returns probs and q for the mismatch classifier."""
+    B, C, T = x_bct.shape
+    flat = x_bct.transpose(1, 2).contiguous().view(-1, C)
+    dist = torch.cdist(flat, codebook)                              # nat.py:2146
+    probs = F.softmax(-dist / temperature, dim=1)                   # nat.py:2153
+    q = torch.empty_like(probs).exponential_(1, generator=generator)
+    idx = torch.argmax(probs / q, dim=-1)                           # nat.py:2154
+    quant = F.embedding(idx, codebook)
+    mse = F.mse_loss(quant, flat)
+    loss = mse + commitment_weight * mse
+    q_ste = flat + (quant - flat)
+    quantized = q_ste.view(B, T, C).transpose(1, 2).contiguous()
+    return quantized, idx.view(B, T), loss, probs, q
+
+
+def rvq_forward_sampling(x: torch.Tensor, codebooks: Sequence[torch.Tensor], temperatures: Sequence[float],
+                         commitment_weight: float = 0.25, generator: torch.Generator = None):
+    """The L-layer chain with per-layer selection: temperature > 0 samples, <= 0 takes the argmin (a layer whose
+    `use_stochastic` is False). Draws from the global CPU generator when `generator` is None, like the reference.
+    Returns (final, codes, losses, aux) where aux[l] = (probs, q) for sampling layers and None otherwise."""
+    x = _as_bct(x, codebooks[0].shape[1])
+    with torch.no_grad():
+        residual = x
+        layers, codes, aux = [], [], []
+        total = 0
+        for cb, t in zip(codebooks, temperatures):
+            if t > 0:
+                quantized, code, loss, probs, q = vq_layer_sampling(residual, cb, t, commitment_weight, generator)
+                aux.append((probs, q))
+            else:
+                quantized, code, loss = vq_layer(residual, cb, commitment_weight)
+                aux.append(None)
+            layers.append(quantized)
+            codes.append(code)
+            total = total + loss
+            residual = residual - quantized
+        final = sum(layers)
+    return final, codes, {"vq_loss": total, "num_layers": len(layers)}, aux
+
+
+def classify_sampling_mismatches(codes_ref: np.ndarray, codes_test: np.ndarray, aux, rel_gap: float =
+                                 SAMPLING_NEAR_TIE_REL_GAP) -> Dict[str, object]:
+    """codes_*: [L, N]. A frame's first differing layer is a near-tie when the reference's own probs / q values of
+    the two codes differ by less than `rel_gap` relatively (the device recomputes the distances exactly, the
+    reference through an fp32 sgemm: their probabilities differ by ~1e-5 relative); later layers of
+    that frame are cascade (the residual and hence every later draw's meaning changed)."""
+    codes_ref = np.asarray(codes_ref).astype(np.int64)
+    codes_test = np.asarray(codes_test).astype(np.int64)
+    L, N = codes_ref.shape
+    diff = codes_ref != codes_test
+    out = {"frames": int(N), "layers": int(L), "exact_frames": int((~diff.any(axis=0)).sum()),
+           "mismatched_tokens": int(diff.sum()), "near_tie_flips": 0, "real_mismatches": 0, "cascade_tokens": 0,
+           "flips": []}
+    for n in np.nonzero(diff.any(axis=0))[0]:
+        first = int(np.argmax(diff[:, n]))
+        if aux[first] is None:
+            kind, gap = "real", float("nan")
+        else:
+            probs, q = aux[first]
+            v = (probs[n].double() / q[n].double()).numpy()
+            a, b = v[codes_ref[first, n]], v[codes_test[first, n]]
+            gap = abs(a - b) / max(abs(a), abs(b), 1e-300)
+            kind = "near_tie" if gap < rel_gap else "real"
+        out["near_tie_flips" if kind == "near_tie" else "real_mismatches"] += 1
+        out["cascade_tokens"] += int(diff[first + 1:, n].sum())
+        out["flips"].append({"frame": int(n), "layer": first, "ref": int(codes_ref[first, n]),
+                             "test": int(codes_test[first, n]), "rel_gap": float(gap), "kind": kind})
+    return out

@@ -51,8 +51,14 @@ def test_shape_errors_are_value_errors_before_any_device_work():
 
 def test_sampling_modes_never_fall_through_to_argmin():
     rvq = ResidualVectorQuantizer(8, 16, 2).eval()                        # default: use_stochastic=True
-    with pytest.raises(NotImplementedError, match="sampling mode"):
+    with pytest.raises(RuntimeError, match="no CPU fallback"):            # native sampling needs the device too
         rvq(torch.randn(1, 8, 4))
+    rvq.sampling_mode = "delegate"
+    with pytest.raises(NotImplementedError, match="delegate"):
+        rvq(torch.randn(1, 8, 4))
+    with pytest.raises(NotImplementedError, match="delegate"):
+        rvq.encode(torch.randn(1, 8, 4))
+    rvq.sampling_mode = "host_noise"
     for q in rvq.quantizers:
         q.use_stochastic = False
     rvq.train()

@@ -102,3 +102,32 @@ def test_pipeline_fixture_is_consistent():
         np.testing.assert_array_equal(got, g[key])
     mel = mel_oracle.mel_power(g["audio"], int(g["sr"]), 2048, 512, 128)
     assert np.abs(mel - g["mel"][0]).max() <= MEL_RTOL_OF_MAX * g["mel"].max() + 1e-6
+
+
+SAMPLING_CASES = ["rvq_sampling_small", "rvq_sampling_mixed", "rvq_sampling_wide"]
+
+
+@pytest.mark.parametrize("name", SAMPLING_CASES)
+def test_sampling_oracle_matches_reference_default_mode(name):
+    """The reference's DEFAULT selection (use_stochastic=True, nat.py:2150-2154) with a seeded global generator:
+    the oracle's spelled-out multinomial (exponential_ then argmax of probs / q) reproduces its codes bit for bit."""
+    g = load_golden(name)
+    x, cbs = torch.from_numpy(g["x"]), [torch.from_numpy(c) for c in g["codebooks"]]
+    torch.manual_seed(int(g["noise_seed"]))
+    quantized, codes, losses, aux = rvq_oracle.rvq_forward_sampling(x, cbs, [float(t) for t in g["temperatures"]])
+    np.testing.assert_array_equal(np.stack([c.numpy() for c in codes]), g["codes"])
+    np.testing.assert_array_equal(quantized.numpy(), g["quantized"])
+    assert abs(float(losses["vq_loss"]) - float(g["vq_loss"])) <= 2e-6 * abs(float(g["vq_loss"]))
+    assert [a is None for a in aux] == [float(t) <= 0 for t in g["temperatures"]]
+
+
+def test_sampling_classifier_flags_real_flip():
+    g = load_golden("rvq_sampling_small")
+    x, cbs = torch.from_numpy(g["x"]), [torch.from_numpy(c) for c in g["codebooks"]]
+    torch.manual_seed(int(g["noise_seed"]))
+    _, codes, _, aux = rvq_oracle.rvq_forward_sampling(x, cbs, [float(t) for t in g["temperatures"]])
+    ref = np.stack([c.numpy().reshape(-1) for c in codes])
+    test = ref.copy()
+    test[0, 3] = (test[0, 3] + 1) % 128
+    rep = rvq_oracle.classify_sampling_mismatches(ref, test, aux)
+    assert rep["real_mismatches"] == 1 and rep["near_tie_flips"] == 0 and rep["flips"][0]["frame"] == 3
