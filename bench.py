@@ -38,7 +38,20 @@ FRAMES = 270_000
 DIM = 768
 CODEBOOK = 1024
 LAYERS_PER_STACK = 4
-CPU_SAMPLE_FRAMES = 32_768
+CPU_BASELINE_FRAMES = 270_000      # cpu_baseline leg: the whole workload once, about 10 s on 16 host threads
+CPU_SAMPLE_FRAMES = 131_072        # --impl reference: one step = this many frames of the same clip (about 4 s)
+
+
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this workload (profiles/stack_traffic.json; bench.py itself never runs under ncu)."""
+    path = os.path.join(ROOT, "profiles", "stack_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"])
+    except (OSError, KeyError, ValueError):
+        return None
 
 
 def measured_peaks():
@@ -315,7 +328,8 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
+                     "frac": achieved / peaks["bf16_tflops_sustained"],
+                     "traffic": ncu_traffic_bytes() if (fused and n_local == FRAMES) else None,
                      "kernel": "rvq_stack_kernel (4 layers per launch: tcgen05 GEMM + candidates + exact decision + "
                                "residual update)" if fused else "rvq_gemm_topk_kernel", "peak_kind": f"{peaks['source']} sustained bf16 (kernel timed "
                      "inside the step)", "frac_of_burst": achieved / peaks["bf16_tflops"],
@@ -326,10 +340,11 @@ def main():
     }
     if not args.no_cpu_baseline and world == 1:
         cores = torch.get_num_threads()
-        rate, sec = cpu_reference_rate(CPU_SAMPLE_FRAMES, steps=1, warmup=0)
+        rate, sec = cpu_reference_rate(min(CPU_BASELINE_FRAMES, n_local), steps=1, warmup=0)
         line["cpu_baseline"] = {"value": rate, "unit": "frames/s", "cores": cores, "kind": "port",
-                                "sample": f"{CPU_SAMPLE_FRAMES} frames of the same workload, one pass, {sec:.1f} s "
-                                          f"(oracle/rvq_oracle.py, torch CPU, {cores} threads)"}
+                                "sample": f"{min(CPU_BASELINE_FRAMES, n_local)} frames of the same workload (all of it), one "
+                                          f"pass, {sec:.1f} s (oracle/rvq_oracle.py, torch CPU, {cores} threads of "
+                                          f"{os.cpu_count()} logical CPUs)"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

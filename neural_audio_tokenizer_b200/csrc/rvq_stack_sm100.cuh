@@ -57,7 +57,8 @@ static_assert(REGS_EPI + (UPD_WARPS / 4) * REGS_UPD + REGS_AUX <= 6 * 80, "setma
 constexpr int TMEM_COLS = 2 * BLOCK_N;
 constexpr int ROWS_PER_UPD_WARP = BLOCK_M / UPD_WARPS;
 constexpr int LCAP = 16;         // eight-code groups listed per frame (compacted when full and at the end)
-constexpr int HCAP = 7;          // candidates handed to the update warps per frame
+constexpr int HCAP = 15;         // candidates handed to the update warps per frame (one 32-byte record: count + 15 indices)
+constexpr int HAND_BYTES = 32;
 constexpr unsigned HAND_SCAN = 0xFFFFu;
 
 #ifndef NAT_STAGES_PAIR
@@ -73,7 +74,7 @@ struct Smem {
     static constexpr int OFF_LIST_S = OFF_B + STAGES * B_BYTES;
     static constexpr int OFF_LIST_I = OFF_LIST_S + LCAP * BLOCK_M * 4;
     static constexpr int OFF_HAND = OFF_LIST_I + LCAP * BLOCK_M * 4;
-    static constexpr int OFF_CN = OFF_HAND + 2 * BLOCK_M * 16;    // [2][BLOCK_N] ||c||^2 of the chunk being scored / the next
+    static constexpr int OFF_CN = OFF_HAND + 2 * BLOCK_M * HAND_BYTES;    // [2][BLOCK_N] ||c||^2 of the chunk being scored / the next
     static constexpr int OFF_BARS = OFF_CN + 2 * BLOCK_N * 4;
     static constexpr int BYTES = OFF_BARS + 256 + 1024 /*alignment slack*/;
     static_assert(BYTES <= 227 * 1024, "shared memory budget");
@@ -230,7 +231,7 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
     uint8_t* smem_b = smem + OFF_B;
     float* list_s = reinterpret_cast<float*>(smem + OFF_LIST_S);                    // [LCAP][128]
     uint32_t* list_i = reinterpret_cast<uint32_t*>(smem + OFF_LIST_I);              // [LCAP][128] group id << 8 | mask
-    uint4* hand = reinterpret_cast<uint4*>(smem + OFF_HAND);                        // [2][128]
+    uint4* hand = reinterpret_cast<uint4*>(smem + OFF_HAND);                        // [2][128] records of two uint4
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
     uint64_t* full = bars;                  // TMA -> MMA
     uint64_t* empty = bars + STAGES;        // MMA -> TMA
@@ -521,7 +522,7 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
                     const long long t1 = w_cempty.begin();
                     mbar_wait(&cempty[slot], ((job >> 1) & 1) ^ 1);
                     w_cempty.end(t1);
-                    const uint32_t hrec = smem_u32(hand) + (slot * BLOCK_M + tid) * 16;
+                    const uint32_t hrec = smem_u32(hand) + (slot * BLOCK_M + tid) * HAND_BYTES;
                     unsigned n = 0;
                     for (int e = 0; e < cnt; ++e) {
                         const uint32_t iv = lds_u32(li + e * (BLOCK_M * 4));
@@ -592,8 +593,9 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
                     const long long t0 = w_cfull.begin();
                     mbar_wait(&cfull[slot], (job >> 1) & 1);
                     w_cfull.end(t0);
+                    // lanes 2 rr and 2 rr + 1 hold the two halves of row rr's record
                     uint4 rec = make_uint4(0u, 0u, 0u, 0u);
-                    if (lane < ROWS_PER_UPD_WARP) rec = hand[slot * BLOCK_M + uw * ROWS_PER_UPD_WARP + lane];
+                    if (lane < 2 * ROWS_PER_UPD_WARP) rec = hand[(slot * BLOCK_M + uw * ROWS_PER_UPD_WARP) * 2 + lane];
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&cempty[slot]);
                     if ((dbg_mode & 15) == 3 || (dbg_mode & 15) == 7) {
@@ -604,19 +606,23 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
 
                     // ---- phase 0: decisions. lane rr ends up holding the code of row rr in jsel.
                     const long long tA = w_dec.begin();
-                    const unsigned n_mine = rec.x & 0xFFFFu;
-                    int jsel = static_cast<int>(rec.x >> 16);
+                    const uint32_t first_word = __shfl_sync(0xffffffffu, rec.x, (lane * 2) & 31);   // row `lane`, word 0
+                    const unsigned n_mine = first_word & 0xFFFFu;
+                    int jsel = static_cast<int>(first_word >> 16);
                     unsigned todo = __ballot_sync(0xffffffffu, lane < nrows && n_mine != 1u);
                     unsigned n_rerank = 0, n_scan = 0;
                     const unsigned n_cert = static_cast<unsigned>(nrows) - __popc(todo);
                     while (todo != 0) {
                         const int rr = __ffs(todo) - 1;
                         todo &= todo - 1;
-                        const uint32_t h0 = __shfl_sync(0xffffffffu, rec.x, rr), h1 = __shfl_sync(0xffffffffu, rec.y, rr),
-                                       h2 = __shfl_sync(0xffffffffu, rec.z, rr), h3 = __shfl_sync(0xffffffffu, rec.w, rr);
-                        const unsigned n = h0 & 0xFFFFu;
-                        const unsigned cidx[HCAP] = {h0 >> 16, h1 & 0xFFFFu, h1 >> 16, h2 & 0xFFFFu,
-                                                     h2 >> 16, h3 & 0xFFFFu, h3 >> 16};
+                        const unsigned n = __shfl_sync(0xffffffffu, rec.x, 2 * rr) & 0xFFFFu;
+                        // candidate c sits in 16-bit slot c + 1 of the record: word (c + 1) / 2 of lanes 2 rr, 2 rr + 1
+                        auto candidate = [&](int c) -> int {
+                            const int w = (c + 1) >> 1;
+                            const uint32_t mine = (w & 3) == 0 ? rec.x : (w & 3) == 1 ? rec.y : (w & 3) == 2 ? rec.z : rec.w;
+                            const uint32_t word = __shfl_sync(0xffffffffu, mine, 2 * rr + (w >> 2));
+                            return static_cast<int>(((c + 1) & 1) ? (word >> 16) : (word & 0xFFFFu));
+                        };
                         float4 rv[NV];
                         load_row<NV>(rv, reinterpret_cast<const float4*>(p.r + static_cast<long long>(row0 + rr) * p.dp), dp4, lane);
                         double best = 0.0;
@@ -634,14 +640,12 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
                             }
                             ++n_scan;
                         } else {
-#pragma unroll
-                            for (int c = 0; c < HCAP; ++c) {
-                                if (c < static_cast<int>(n)) {                      // warp-uniform
-                                    const int k = min(static_cast<int>(cidx[c]), p.K - 1);
-                                    const double s = score_regs<NV>(rv, reinterpret_cast<const float4*>(cb_l + static_cast<long long>(k) * p.dp),
-                                                                    dp4, cn64_l[k], lane);
-                                    if (bestj < 0 || s < best || (s == best && k < bestj)) { best = s; bestj = k; }
-                                }
+#pragma unroll 1
+                            for (int c = 0; c < static_cast<int>(n); ++c) {        // warp-uniform trip count, <= HCAP
+                                const int k = min(candidate(c), p.K - 1);
+                                const double s = score_regs<NV>(rv, reinterpret_cast<const float4*>(cb_l + static_cast<long long>(k) * p.dp),
+                                                                dp4, cn64_l[k], lane);
+                                if (bestj < 0 || s < best || (s == best && k < bestj)) { best = s; bestj = k; }
                             }
                             ++n_rerank;
                         }

@@ -227,8 +227,12 @@ def test_errors_and_modes():
     from neural_audio_tokenizer_b200 import ResidualVectorQuantizer
     rvq = ResidualVectorQuantizer(32, 64, 2).cuda().eval()           # reference default: use_stochastic=True
     x = torch.randn(1, 32, 10, device="cuda")
+    sampled = rvq(x)                                                  # eval-mode sampling runs natively now
+    assert len(sampled[1]) == 2 and sampled[1][0].shape == (1, 10)    # (tests/test_rvq_sampling_gpu.py checks the codes)
+    rvq.sampling_mode = "delegate"
     with pytest.raises(NotImplementedError):
         rvq(x)
+    rvq.sampling_mode = "host_noise"
     for q in rvq.quantizers:
         q.use_stochastic = False
     with pytest.raises(NotImplementedError):
