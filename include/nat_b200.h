@@ -194,6 +194,23 @@ int nat_ndjson_emit_frames(const void* sem_codes_host, const void* ac_codes_host
 void nat_free_host(void* p);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Token statistics over the index streams
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* counts_dev[v] += #{tokens == v} for 0 <= v < vocab (uint64 [vocab], ACCUMULATED: call once per stream to pool
+ * layers, caller zeroes); tokens outside [0, vocab) are added to *outliers_dev. Replaces the `torch.unique` passes of
+ * the diversity and entropy figures (nat.py:4913-4917, 3442-3447, 3577-3584): unique tokens = non-zero bins, counts =
+ * the bins themselves. */
+int nat_token_histogram(const void* codes_dev, int code_dtype, int64_t n_tokens, int vocab,
+                        unsigned long long* counts_dev, unsigned long long* outliers_dev, void* stream);
+
+/* hist_dev[i * bins + j] += #{n : a[n] in bin i, b[n] in bin j} with numpy.histogram2d's binning over the given
+ * float64 edges (bins + 1 each, device memory), bins <= 64: the integer part of _calculate_mutual_information
+ * (nat.py:3586-3637). uint64 [bins, bins], ACCUMULATED. */
+int nat_token_joint_histogram(const void* a_dev, const void* b_dev, int code_dtype, int64_t n, const double* edges_a_dev,
+                              const double* edges_b_dev, int bins, unsigned long long* hist_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Debug / validation hooks (used by tests/; not part of the drop-in surface)
  * ------------------------------------------------------------------------------------------------------------- */
 

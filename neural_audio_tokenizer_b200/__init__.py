@@ -11,7 +11,8 @@ from .install import install, patch_reference_module
 from .ndjson import create_ndjson_stream, emit_frame_lines
 from .quantizers import ResidualVectorQuantizer, VectorQuantizer
 from .sharding import all_gather_codes, shard_range
+from . import token_stats
 
 __all__ = ["ResidualVectorQuantizer", "VectorQuantizer", "MelSpectrogram", "spectral_stats", "install",
-           "patch_reference_module", "all_gather_codes", "shard_range", "create_ndjson_stream", "emit_frame_lines"]
+           "patch_reference_module", "all_gather_codes", "shard_range", "create_ndjson_stream", "emit_frame_lines", "token_stats"]
 __version__ = "0.1.0"

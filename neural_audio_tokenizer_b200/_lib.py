@@ -47,6 +47,8 @@ _SIGNATURES = [
     ("nat_spectral_num_frames", c_int64, [c_int64, c_int, c_int]),
     ("nat_debug_rvq_scores", c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_size_t, c_void_p]),
+    ("nat_token_histogram", c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    ("nat_token_joint_histogram", c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     ("nat_ndjson_emit_frames", c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_int, c_int, c_int,
                                        c_char_p, ctypes.c_double, POINTER(c_void_p), POINTER(c_size_t)]),
     ("nat_free_host", None, [c_void_p]),

@@ -24,6 +24,7 @@
 #include "rvq_prepare.cuh"
 #include "rvq_rows.cuh"
 #include "rvq_stack_sm100.cuh"
+#include "token_stats.cuh"
 
 namespace {
 
@@ -643,6 +644,48 @@ int nat_rvq_decode_f32(const nat_rvq_codebooks* cb, const void* codes_dev, int c
     const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, cb->sm_count * 16));
     NAT_LAUNCH(5, static_cast<cudaStream_t>(stream), rows::decode_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         cb->cbf, static_cast<long long>(cb->K) * cb->dp, cb->dp, cb->D, used, codes_dev, code_dtype, N, T, layout, out_dev));
+    NAT_CUDA(cudaGetLastError());
+    return NAT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- token statistics
+int nat_token_histogram(const void* codes_dev, int code_dtype, int64_t n_tokens, int vocab,
+                        unsigned long long* counts_dev, unsigned long long* outliers_dev, void* stream) {
+    using namespace nat;
+    if (code_dtype < NAT_CODES_I64 || code_dtype > NAT_CODES_I16) return fail(NAT_ERR_INVALID_ARGUMENT, "bad code dtype %d", code_dtype);
+    if (vocab < 1 || n_tokens < 0) return fail(NAT_ERR_INVALID_ARGUMENT, "bad vocabulary size or token count");
+    if (counts_dev == nullptr || outliers_dev == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null output");
+    if (n_tokens == 0) return NAT_OK;
+    if (codes_dev == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null codes");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int dev = 0, sms = 148;
+    NAT_CUDA(cudaGetDevice(&dev));
+    NAT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const size_t smem = vocab <= stats::kHistSmemBins ? static_cast<size_t>(vocab) * 4 : 0;
+    const long long want = (n_tokens + stats::kHistThreads * 8 - 1) / (stats::kHistThreads * 8);
+    const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(want, sms * 4)));
+    NAT_LAUNCH(5, st, stats::token_histogram_kernel<<<grid, stats::kHistThreads, smem, st>>>(
+        codes_dev, code_dtype, n_tokens, vocab, counts_dev, outliers_dev));
+    NAT_CUDA(cudaGetLastError());
+    return NAT_OK;
+}
+
+int nat_token_joint_histogram(const void* a_dev, const void* b_dev, int code_dtype, int64_t n, const double* edges_a_dev,
+                              const double* edges_b_dev, int bins, unsigned long long* hist_dev, void* stream) {
+    using namespace nat;
+    if (code_dtype < NAT_CODES_I64 || code_dtype > NAT_CODES_I16) return fail(NAT_ERR_INVALID_ARGUMENT, "bad code dtype %d", code_dtype);
+    if (bins < 1 || bins > stats::kJointMaxBins) return fail(NAT_ERR_UNSUPPORTED, "bins must be in [1, %d], got %d", stats::kJointMaxBins, bins);
+    if (n < 0 || hist_dev == nullptr || edges_a_dev == nullptr || edges_b_dev == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "bad argument");
+    if (n == 0) return NAT_OK;
+    if (a_dev == nullptr || b_dev == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null codes");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int dev = 0, sms = 148;
+    NAT_CUDA(cudaGetDevice(&dev));
+    NAT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const long long want = (n + stats::kJointThreads * 8 - 1) / (stats::kJointThreads * 8);
+    const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(want, sms * 4)));
+    NAT_LAUNCH(5, st, stats::joint_histogram_kernel<<<grid, stats::kJointThreads, 0, st>>>(
+        a_dev, b_dev, code_dtype, n, edges_a_dev, edges_b_dev, bins, hist_dev));
     NAT_CUDA(cudaGetLastError());
     return NAT_OK;
 }

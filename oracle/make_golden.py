@@ -228,6 +228,31 @@ def ndjson_cases(nat) -> None:
     print("ndjson_cases:", {k: len(v["body"]) for k, v in cases.items()})
 
 
+def token_stats_cases(nat) -> None:
+    """Diversity / entropy / mutual information from the reference's own TokenizationEvaluator on seeded streams."""
+    ev = nat.TokenizationEvaluator(sample_rate=22050)
+    cases = {}
+    specs = [("uniform_1024", 1024, 5000, 0.0), ("sticky_1024", 1024, 4000, 0.9), ("narrow_40", 40, 3000, 0.5),
+             ("constant", 1024, 500, 1.0), ("two_values", 2, 777, 0.3)]
+    for name, vocab, n, stick in specs:
+        rng = np.random.default_rng(sum(map(ord, name)))
+        sem = [sticky_stream(rng, n, vocab, stick) for _ in range(4)]
+        ac = [sticky_stream(rng, n - 7 * i, vocab, stick * 0.5) for i in range(4)]        # ragged lengths
+        sem_t = [torch.from_numpy(s)[None] for s in sem]
+        ac_t = [torch.from_numpy(a)[None] for a in ac]
+        all_s = torch.cat([c.flatten().long() for c in sem_t])
+        all_a = torch.cat([c.flatten().long() for c in ac_t])
+        cases[name] = {
+            "vocab": vocab, "semantic": [s.tolist() for s in sem], "acoustic": [a.tolist() for a in ac],
+            "semantic_diversity": len(torch.unique(all_s)) / len(all_s),          # nat.py:4916
+            "acoustic_diversity": len(torch.unique(all_a)) / len(all_a),
+            "semantic_entropy": ev._calculate_entropy(all_s), "acoustic_entropy": ev._calculate_entropy(all_a),
+            "mutual_information": ev._calculate_mutual_information(all_s, all_a)}
+    with open(os.path.join(GOLDEN, "token_stats.json"), "w") as f:
+        json.dump(cases, f, separators=(",", ":"))
+    print("token_stats:", {k: (round(v["semantic_entropy"], 4), round(v["mutual_information"], 4)) for k, v in cases.items()})
+
+
 def sampling_cases(nat) -> None:
     rvq_sampling_case(nat, "rvq_sampling_small", seed=7, D=64, K=128, L=4, T=300, noise_seed=99)
     rvq_sampling_case(nat, "rvq_sampling_mixed", seed=8, D=48, K=100, L=4, T=120, noise_seed=5, argmin_layers=(1, 3))
@@ -243,6 +268,9 @@ def main() -> None:
         return
     if "sampling" in sys.argv[1:]:
         sampling_cases(nat)
+        return
+    if "stats" in sys.argv[1:]:
+        token_stats_cases(nat)
         return
     rvq_case(nat, "rvq_small", seed=7, D=64, K=128, L=4, B=1, T=50, store_codebooks=True)
     rvq_case(nat, "rvq_ragged", seed=11, D=80, K=300, L=3, B=2, T=37, store_codebooks=True)
@@ -267,6 +295,7 @@ def main() -> None:
     pipeline_case(nat, "pipeline_tone_argmin")
     ndjson_cases(nat)
     sampling_cases(nat)
+    token_stats_cases(nat)
 
 
 if __name__ == "__main__":
