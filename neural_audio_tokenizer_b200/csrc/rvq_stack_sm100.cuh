@@ -575,6 +575,8 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
                 const float cabs = __ldg(&p.lc[l].cabs);
                 double* loss_l = p.row_loss != nullptr ? p.row_loss + static_cast<long long>(l) * p.loss_ld : nullptr;
                 const bool residual_needed = !last || loss_l != nullptr;
+                // the hot update form of the previous layer skipped its write-back (see keep_r below)
+                const bool replay_prev = last && p.L >= 2 && p.row_loss == nullptr && dp4 == NV * 32;
                 char* codes_l = static_cast<char*>(p.codes);
                 const long long code_base = static_cast<long long>(l) * p.codes_ld + p.code_off;
                 for (int i = g0; i < g0 + gs; ++i, ++job) {
@@ -625,6 +627,22 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
                         };
                         float4 rv[NV];
                         load_row<NV>(rv, reinterpret_cast<const float4*>(p.r + static_cast<long long>(row0 + rr) * p.dp), dp4, lane);
+                        if (replay_prev) {
+                            // the stored row is still the residual that ENTERED the previous layer (its update was
+                            // not written back): redo that update here, same three fp32 ops, from the emitted code
+                            const int jp = rows::load_code(codes_l, p.code_dtype, code_base - p.codes_ld + row0 + rr);
+                            const float4* cp4 = reinterpret_cast<const float4*>(cb_l - static_cast<long long>(p.K) * p.dp +
+                                                                               static_cast<long long>(jp) * p.dp);
+#pragma unroll
+                            for (int k = 0; k < NV; ++k) {
+                                const float4 cv = __ldcg(cp4 + k * 32 + lane);
+                                float t;
+                                t = __fsub_rn(cv.x, rv[k].x); rv[k].x = __fsub_rn(rv[k].x, __fadd_rn(rv[k].x, t));
+                                t = __fsub_rn(cv.y, rv[k].y); rv[k].y = __fsub_rn(rv[k].y, __fadd_rn(rv[k].y, t));
+                                t = __fsub_rn(cv.z, rv[k].z); rv[k].z = __fsub_rn(rv[k].z, __fadd_rn(rv[k].z, t));
+                                t = __fsub_rn(cv.w, rv[k].w); rv[k].w = __fsub_rn(rv[k].w, __fadd_rn(rv[k].w, t));
+                            }
+                        }
                         double best = 0.0;
                         int bestj = -1;
                         if (n == HAND_SCAN) {
@@ -660,6 +678,9 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
                     if (!last && loss_l == nullptr && dp4 == NV * 32 && nrows > 0) {
                         // Hot form: every lane holds exactly NV float4 of a row, nothing is predicated. One row at a
                         // time per warp; the sixteen update warps of the CTA cover each other's memory latency.
+                        // The residual entering the LAST layer is only ever seen through its fp16 operand (the last
+                        // layer emits codes and, without a loss, nothing else): it is not written back.
+                        const bool keep_r = l + 2 < p.L;
 #pragma unroll 1
                         for (int rr = 0; rr < nrows; ++rr) {
                             const int row = row0 + rr;
@@ -685,7 +706,7 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
                                 const float2 c01 = make_float2(cv[k].x, cv[k].y), c23 = make_float2(cv[k].z, cv[k].w);
                                 const float2 t01 = sub2(c01, x01), t23 = sub2(c23, x23);
                                 const float2 n01 = sub2(x01, __fadd2_rn(x01, t01)), n23 = sub2(x23, __fadd2_rn(x23, t23));
-                                r4[k * 32 + lane] = make_float4(n01.x, n01.y, n23.x, n23.y);
+                                if (keep_r) r4[k * 32 + lane] = make_float4(n01.x, n01.y, n23.x, n23.y);
                                 amax = fmaxf(fmaxf(amax, fabsf(n01.x)), fmaxf(fabsf(n01.y), fmaxf(fabsf(n23.x), fabsf(n23.y))));
                                 const float2 s01 = __fmul2_rn(n01, sx2), s23 = __fmul2_rn(n23, sx2);
                                 const __half2 h01 = __float22half2_rn(s01), h23 = __float22half2_rn(s23);
