@@ -411,6 +411,11 @@ static int encode_chunk(const EncodeCall& c, const Workspace& ws, const CUtensor
         sa.code_dtype = c.code_dtype;
         sa.dbg = cb->stack_dbg_on ? cb->stack_dbg : nullptr;
         { const char* e = getenv("NAT_RVQ_DBG_MODE"); sa.dbg_mode = e ? atoi(e) : 0; }
+        // Residual write-back policy of the hot update form: the residual entering the last layer is never needed in
+        // memory (only its fp16 operand is), and writing back after every other layer only (later layers replay the
+        // skipped update from the emitted code, one extra L2 gather) measured faster than every layer or none.
+        sa.store_mask = 0x55555555 & ((1 << std::max(0, cb->L - 2)) - 1);
+        { const char* e = getenv("NAT_RVQ_STORE_MASK"); if (e) sa.store_mask &= atoi(e); }
         // CTA pairs (one tcgen05.mma.cta_group::2 per two SMs) once there is more than one tile; NAT_RVQ_PAIR=1 keeps
         // the single-CTA form for A/B measurements.
         const int pair = (n_tiles >= 2 && cb->sm_count >= 2 && fused_pair()) ? 2 : 1;

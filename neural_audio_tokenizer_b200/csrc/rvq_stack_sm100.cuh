@@ -98,6 +98,8 @@ struct StackArgs {
     unsigned long long* stats;   // [L, 4] counters or nullptr
     int n_rows, n_tiles, L, K, kp, dp, code_dtype;
     int group;                   // tiles per group (>= 1); >= tiles per CTA means plain layer-major order
+    int store_mask;              // bit l: the residual leaving layer l is written back (hot form only; a clear bit
+                                 // means later layers replay that update from the emitted code instead)
     int dbg_mode;                // timing experiments only (results invalid when != 0)
     unsigned long long* dbg;     // optional [grid][DBG_SLOTS] cycle counters (nat_debug_stack_counters), or nullptr
 };
@@ -197,6 +199,19 @@ __device__ __forceinline__ void load_code(float4 (&cv)[NV], const float4* __rest
     for (int k = 0; k < NV; ++k) {
         const int q = k * 32 + lane;
         cv[k] = q < dp4 ? __ldcg(c4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+// r <- r - (r + (c - r)) for one code vector: the reference's update (nat.py:2159, 2167, 1405) on a row held in registers.
+template <int NV>
+__device__ __forceinline__ void replay_update(float4 (&rv)[NV], const float4* __restrict__ c4, int lane) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const float4 cv = __ldcg(c4 + k * 32 + lane);
+        float t;
+        t = __fsub_rn(cv.x, rv[k].x); rv[k].x = __fsub_rn(rv[k].x, __fadd_rn(rv[k].x, t));
+        t = __fsub_rn(cv.y, rv[k].y); rv[k].y = __fsub_rn(rv[k].y, __fadd_rn(rv[k].y, t));
+        t = __fsub_rn(cv.z, rv[k].z); rv[k].z = __fsub_rn(rv[k].z, __fadd_rn(rv[k].z, t));
+        t = __fsub_rn(cv.w, rv[k].w); rv[k].w = __fsub_rn(rv[k].w, __fadd_rn(rv[k].w, t));
     }
 }
 // a - b on both halves, rounded exactly like two __fsub_rn (one fused multiply by -1, one rounding)
@@ -575,8 +590,11 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
                 const float cabs = __ldg(&p.lc[l].cabs);
                 double* loss_l = p.row_loss != nullptr ? p.row_loss + static_cast<long long>(l) * p.loss_ld : nullptr;
                 const bool residual_needed = !last || loss_l != nullptr;
-                // the hot update form of the previous layer skipped its write-back (see keep_r below)
-                const bool replay_prev = last && p.L >= 2 && p.row_loss == nullptr && dp4 == NV * 32;
+                // Hot form only: layers whose store bit is clear did not write their residual back; the stored row is the
+                // one that entered the oldest such layer, and this layer replays their updates from the emitted codes.
+                const int store_mask = (p.row_loss == nullptr && dp4 == NV * 32) ? p.store_mask : ~0;
+                int n_replay = 0;
+                for (int jj = l - 1; jj >= 0 && !((store_mask >> jj) & 1); --jj) ++n_replay;
                 char* codes_l = static_cast<char*>(p.codes);
                 const long long code_base = static_cast<long long>(l) * p.codes_ld + p.code_off;
                 for (int i = g0; i < g0 + gs; ++i, ++job) {
@@ -627,20 +645,14 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
                         };
                         float4 rv[NV];
                         load_row<NV>(rv, reinterpret_cast<const float4*>(p.r + static_cast<long long>(row0 + rr) * p.dp), dp4, lane);
-                        if (replay_prev) {
-                            // the stored row is still the residual that ENTERED the previous layer (its update was
-                            // not written back): redo that update here, same three fp32 ops, from the emitted code
-                            const int jp = rows::load_code(codes_l, p.code_dtype, code_base - p.codes_ld + row0 + rr);
-                            const float4* cp4 = reinterpret_cast<const float4*>(cb_l - static_cast<long long>(p.K) * p.dp +
-                                                                               static_cast<long long>(jp) * p.dp);
-#pragma unroll
-                            for (int k = 0; k < NV; ++k) {
-                                const float4 cv = __ldcg(cp4 + k * 32 + lane);
-                                float t;
-                                t = __fsub_rn(cv.x, rv[k].x); rv[k].x = __fsub_rn(rv[k].x, __fadd_rn(rv[k].x, t));
-                                t = __fsub_rn(cv.y, rv[k].y); rv[k].y = __fsub_rn(rv[k].y, __fadd_rn(rv[k].y, t));
-                                t = __fsub_rn(cv.z, rv[k].z); rv[k].z = __fsub_rn(rv[k].z, __fadd_rn(rv[k].z, t));
-                                t = __fsub_rn(cv.w, rv[k].w); rv[k].w = __fsub_rn(rv[k].w, __fadd_rn(rv[k].w, t));
+                        if constexpr (true) {
+#pragma unroll 1
+                            for (int back = n_replay; back > 0; --back) {
+                                const int jp = rows::load_code(codes_l, p.code_dtype,
+                                                               code_base - back * p.codes_ld + row0 + rr);
+                                if (dp4 == NV * 32)
+                                    replay_update<NV>(rv, reinterpret_cast<const float4*>(
+                                        cb_l + (static_cast<long long>(jp) - static_cast<long long>(back) * p.K) * p.dp), lane);
                             }
                         }
                         double best = 0.0;
@@ -680,7 +692,7 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
                         // time per warp; the sixteen update warps of the CTA cover each other's memory latency.
                         // The residual entering the LAST layer is only ever seen through its fp16 operand (the last
                         // layer emits codes and, without a loss, nothing else): it is not written back.
-                        const bool keep_r = l + 2 < p.L;
+                        const bool keep_r = (store_mask >> l) & 1;
 #pragma unroll 1
                         for (int rr = 0; rr < nrows; ++rr) {
                             const int row = row0 + rr;
@@ -690,6 +702,12 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
                             float4 cur[NV], cv[NV];
 #pragma unroll
                             for (int k = 0; k < NV; ++k) cur[k] = __ldcg(r4 + k * 32 + lane);
+#pragma unroll 1
+                            for (int back = n_replay; back > 0; --back) {
+                                const int jp = rows::load_code(codes_l, p.code_dtype, code_base - back * p.codes_ld + row);
+                                replay_update<NV>(cur, reinterpret_cast<const float4*>(
+                                    cb_l + (static_cast<long long>(jp) - static_cast<long long>(back) * p.K) * p.dp), lane);
+                            }
 #pragma unroll
                             for (int k = 0; k < NV; ++k) cv[k] = __ldcg(c4 + k * 32 + lane);
                             // operand scale from the bound  max|r'| <= max|r| + max|c|
