@@ -465,37 +465,48 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
                         const int gid0 = (chunk * BLOCK_N) >> 3;
 
                         // FILTER = false: running minimum only.  FILTER = true: minimum + list of groups in the window.
+                        // All 32 scores and the four eight-group minima are formed first (independent instructions), and
+                        // ONE test against the threshold guards the list code: thr only ever shrinks, so a block whose
+                        // smallest score is above it has no entry to add. Inside, the groups are taken in order with the
+                        // threshold updated after each entry, exactly as if they had been tested one by one.
                         auto scan32 = [&](const uint32_t (&v)[32], int g, bool filter) {
-                            float4 cq[8];
-#pragma unroll
-                            for (int h = 0; h < 8; ++h) cq[h] = lds_f32x4(cn_s + (g * 32 + h * 4) * 4);
+                            float s[32];
+                            float mn[4];
 #pragma unroll
                             for (int h = 0; h < 4; ++h) {
-                                const float4 c0 = cq[h * 2], c1 = cq[h * 2 + 1];
-                                float s[8];
-                                s[0] = fmaf(__uint_as_float(v[h * 8 + 0]), alpha, c0.x);
-                                s[1] = fmaf(__uint_as_float(v[h * 8 + 1]), alpha, c0.y);
-                                s[2] = fmaf(__uint_as_float(v[h * 8 + 2]), alpha, c0.z);
-                                s[3] = fmaf(__uint_as_float(v[h * 8 + 3]), alpha, c0.w);
-                                s[4] = fmaf(__uint_as_float(v[h * 8 + 4]), alpha, c1.x);
-                                s[5] = fmaf(__uint_as_float(v[h * 8 + 5]), alpha, c1.y);
-                                s[6] = fmaf(__uint_as_float(v[h * 8 + 6]), alpha, c1.z);
-                                s[7] = fmaf(__uint_as_float(v[h * 8 + 7]), alpha, c1.w);
-                                const float mn = fminf(fminf(fminf(fminf(s[0], s[1]), s[2]), fminf(fminf(s[3], s[4]), s[5])),
-                                                       fminf(fminf(s[6], s[7]), inf));
-                                if (!filter) {
-                                    m = fminf(m, mn);
-                                } else if (mn <= thr) {
+                                const float4 c0 = lds_f32x4(cn_s + (g * 32 + h * 8) * 4);
+                                const float4 c1 = lds_f32x4(cn_s + (g * 32 + h * 8 + 4) * 4);
+                                s[h * 8 + 0] = fmaf(__uint_as_float(v[h * 8 + 0]), alpha, c0.x);
+                                s[h * 8 + 1] = fmaf(__uint_as_float(v[h * 8 + 1]), alpha, c0.y);
+                                s[h * 8 + 2] = fmaf(__uint_as_float(v[h * 8 + 2]), alpha, c0.z);
+                                s[h * 8 + 3] = fmaf(__uint_as_float(v[h * 8 + 3]), alpha, c0.w);
+                                s[h * 8 + 4] = fmaf(__uint_as_float(v[h * 8 + 4]), alpha, c1.x);
+                                s[h * 8 + 5] = fmaf(__uint_as_float(v[h * 8 + 5]), alpha, c1.y);
+                                s[h * 8 + 6] = fmaf(__uint_as_float(v[h * 8 + 6]), alpha, c1.z);
+                                s[h * 8 + 7] = fmaf(__uint_as_float(v[h * 8 + 7]), alpha, c1.w);
+                                mn[h] = fminf(fminf(fminf(fminf(s[h * 8 + 0], s[h * 8 + 1]), s[h * 8 + 2]),
+                                                    fminf(fminf(s[h * 8 + 3], s[h * 8 + 4]), s[h * 8 + 5])),
+                                              fminf(fminf(s[h * 8 + 6], s[h * 8 + 7]), inf));
+                            }
+                            const float mall = fminf(fminf(mn[0], mn[1]), fminf(mn[2], mn[3]));
+                            if (!filter) {
+                                m = fminf(m, mall);
+                                return;
+                            }
+                            if (!(mall <= thr)) return;
+#pragma unroll
+                            for (int h = 0; h < 4; ++h) {
+                                if (mn[h] <= thr) {
                                     if (DBG) ++n_events;
-                                    m = fminf(m, mn);
+                                    m = fminf(m, mn[h]);
                                     // m + W rounded up: the kept set must be a superset of the exact window
                                     thr = fmaf(fabsf(m) + window, 2.4e-7f, m + window);
                                     uint32_t mask = 0;
 #pragma unroll
-                                    for (int e = 0; e < 8; ++e) mask |= (s[e] <= thr) ? (1u << e) : 0u;
+                                    for (int e = 0; e < 8; ++e) mask |= (s[h * 8 + e] <= thr) ? (1u << e) : 0u;
                                     if (cnt == LCAP) compact();
                                     if (cnt < LCAP) {
-                                        sts_f32(ls + cnt * (BLOCK_M * 4), mn);
+                                        sts_f32(ls + cnt * (BLOCK_M * 4), mn[h]);
                                         sts_u32(li + cnt * (BLOCK_M * 4),
                                                 (static_cast<uint32_t>(gid0 + g * 4 + h) << 8) | mask);
                                         ++cnt;

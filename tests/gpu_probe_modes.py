@@ -30,4 +30,4 @@ for group in os.environ.get("PROBE_GROUPS", "2").split(","):
             _lib.check(lib.nat_debug_stack_counters(h, 0, buf.ctypes.data_as(ctypes.c_void_p), nc.value, None, None))
         avg = buf.astype(np.float64).mean(axis=0)
         print(f"group={group} mode={mode} ms(prep+stack)={e0.elapsed_time(e1):.3f} kcycles/CTA:",
-              {n: int(avg[i] / 1e3) for i, n in enumerate(names)}, flush=True)
+              {n: int(avg[i] / 1e3) for i, n in enumerate(names)}, "events_per_frame_layer(thread 0)", round(avg[11] / (4 * ((N + 127) // 128 + 147) // 148), 2), flush=True)
