@@ -28,6 +28,9 @@
 #include "nat_common.cuh"
 #include "rvq_rows.cuh"
 
+#ifndef NAT_UPD_WARPS
+#define NAT_UPD_WARPS 16
+#endif
 #ifndef NAT_REGS_EPI
 #define NAT_REGS_EPI 88
 #define NAT_REGS_UPD 88
@@ -44,16 +47,20 @@ constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
 constexpr int EPI_WARPS = 4;
-constexpr int UPD_WARPS = 16;
+constexpr int UPD_WARPS = NAT_UPD_WARPS;
 constexpr int WARP_EPI0 = 0;
 constexpr int WARP_UPD0 = EPI_WARPS;
 constexpr int WARP_TMA = EPI_WARPS + UPD_WARPS;
 constexpr int WARP_MMA = WARP_TMA + 1;
-constexpr int NUM_THREADS = 768;  // six warpgroups: candidates | 4 x update | TMA, MMA and two idle warps
-// 80 registers per thread at launch; after setmaxnreg: 128 * (104 + 4 * 88 + 40) <= 64 K
+constexpr int NUM_THREADS = (EPI_WARPS + UPD_WARPS + 4) * 32;  // warpgroups: candidates | update ... | TMA, MMA and two idle warps
+constexpr int LAUNCH_REGS = (65536 / NUM_THREADS) / 8 * 8;     // registers per thread the launch bound leaves ptxas
+// 80 registers per thread at launch (768 threads); after setmaxnreg: 128 * (88 + 4 * 88 + 40) <= 64 K.
+// NAT_UPD_WARPS / NAT_REGS_* are A/B build knobs: 8 update warps with 120 registers measured 12 % slower than 16 with 88
+// (the update is bound by rows in flight, not by registers).
 constexpr int REGS_EPI = NAT_REGS_EPI, REGS_UPD = NAT_REGS_UPD, REGS_AUX = 40;
-static_assert(WARP_MMA + 1 <= NUM_THREADS / 32 && EPI_WARPS == 4 && UPD_WARPS == 16, "warpgroup layout");
-static_assert(REGS_EPI + (UPD_WARPS / 4) * REGS_UPD + REGS_AUX <= 6 * 80, "setmaxnreg only moves registers inside the CTA: the total must not exceed the launch allocation");
+static_assert(WARP_MMA + 1 <= NUM_THREADS / 32 && EPI_WARPS == 4 && UPD_WARPS % 4 == 0 && BLOCK_M % UPD_WARPS == 0 &&
+              2 * (BLOCK_M / UPD_WARPS) <= 32, "warpgroup layout");
+static_assert(REGS_EPI + (UPD_WARPS / 4) * REGS_UPD + REGS_AUX <= (NUM_THREADS / 128) * LAUNCH_REGS, "setmaxnreg only moves registers inside the CTA: the total must not exceed the launch allocation");
 constexpr int TMEM_COLS = 2 * BLOCK_N;
 constexpr int ROWS_PER_UPD_WARP = BLOCK_M / UPD_WARPS;
 constexpr int LCAP = 16;         // eight-code groups listed per frame (compacted when full and at the end)
@@ -392,7 +399,8 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
         }
         __syncwarp();
     } else if (warp < WARP_UPD0) {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
+        if (REGS_EPI > LAUNCH_REGS) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
+        else if (REGS_EPI < LAUNCH_REGS) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
         // ------------------------------------------------------------------ candidates: one frame per thread
         // Scores are looked at eight at a time. Chunk 0 is read twice: first only for its minimum (branch-free), so
         // that the filter pass starts with a threshold that is already within a few records of the final one; every
@@ -579,7 +587,8 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
             d[DBG_EPI_EVENTS] = n_events;
         }
     } else if (warp < WARP_TMA) {
-        if (REGS_UPD > 80) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_UPD));
+        if (REGS_UPD > LAUNCH_REGS) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_UPD));
+        else if (REGS_UPD < LAUNCH_REGS) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_UPD));
         // ------------------------------------------------------------------ update: one warp per frame
         // Phase 0 settles the frames the coarse pass could not certify (exact fp64 re-rank, or the exact scan).
         // Phase 1 is branch-free: row rr+1's residual and code vector are in flight while row rr is updated, and the
