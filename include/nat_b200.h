@@ -111,13 +111,15 @@ int nat_rvq_encode_f32(const nat_rvq_codebooks* cb, const float* x_dev, int layo
  *                      reference makes them (one `empty_like(probs).exponential_(1)` per layer from torch's CPU
  *                      generator) -- codes then equal the reference's except at near-ties of probs / q; or NULL:
  *                      q comes from Philox4x32-10 keyed by philox_seed (counter: frame, code, philox_draw + layer),
- *                      equal to the reference in distribution only
+ *                      equal to the reference in distribution only. In this mode the distances come from the
+ *                      tensor-core pass (bulk throughput; a score matrix of B*T x K floats is allocated stream-ordered)
+ *                      unless flags has NAT_RVQ_EXACT_SCAN, which keeps the exact per-frame scan
  * Outputs as nat_rvq_encode_f32. */
 int nat_rvq_sample_f32(const nat_rvq_codebooks* cb, const float* x_dev, int layout, int64_t B, int64_t T,
                        void* codes_out_dev, int code_dtype, float* quantized_out_dev, float* loss_out_dev,
                        float commitment_weight, const float* temperatures_host, const float* noise_dev,
                        unsigned long long philox_seed, unsigned long long philox_draw,
-                       void* workspace_dev, size_t workspace_bytes, void* stream);
+                       void* workspace_dev, size_t workspace_bytes, int flags, void* stream);
 
 /* Same call, timed: CUDA events around every kernel launch on `stream`, then a stream synchronise, and the summed
  * device milliseconds per kernel class in prof_ms_host[NAT_PROF_FIELDS] (bench.py's roofline leg; not a hot path). */

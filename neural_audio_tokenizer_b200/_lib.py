@@ -33,7 +33,7 @@ _SIGNATURES = [
                                    c_float, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     ("nat_rvq_sample_f32", c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_int, c_void_p, c_void_p,
                                    c_float, POINTER(c_float), c_void_p, ctypes.c_uint64, ctypes.c_uint64, c_void_p,
-                                   c_size_t, c_void_p]),
+                                   c_size_t, c_int, c_void_p]),
     ("nat_rvq_encode_profile_f32", c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_int, c_void_p,
                                            c_void_p, c_float, c_void_p, c_void_p, c_size_t, c_int, c_void_p,
                                            POINTER(c_float)]),

@@ -388,6 +388,7 @@ struct EncodeCall {
     // host-drawn noise [L, N, K], Philox key / draw base otherwise
     const float* temperatures = nullptr; const float* noise = nullptr;
     unsigned long long seed = 0, draw_base = 0;
+    float* scores = nullptr;       // [chunk rows, kp] accumulator dump of the Philox fast path (stream-ordered allocation)
 };
 
 static int encode_chunk(const EncodeCall& c, const Workspace& ws, const CUtensorMap& map_a, long long n0, int n,
@@ -457,8 +458,18 @@ static int encode_chunk(const EncodeCall& c, const Workspace& ws, const CUtensor
             sargs.row0 = static_cast<unsigned long long>(n0);
             sargs.draw = static_cast<unsigned>(c.draw_base + l);
             sargs.temperature = c.temperatures[l];
-            const size_t smem = scan_smem + static_cast<size_t>(cb->K) * sizeof(float);
-            NAT_LAUNCH(3, st, rows::sample_scan_kernel<<<std::min(n, scan_grid), rows::kScanThreads, smem, st>>>(ua, sargs));
+            if (c.noise == nullptr && !c.exact && c.scores != nullptr) {
+                // Philox noise: distances from the tensor-core pass (score matrix through HBM), one warp per frame
+                NAT_LAUNCH(1, st, gemm::rvq_gemm_topk_kernel<true><<<std::min(n_tiles, cb->sm_count), gemm::NUM_THREADS,
+                                                                  gemm::SMEM_BYTES, st>>>(
+                    map_a, cb->map_b, n, n_tiles, cb->kp / gemm::BLOCK_N, cb->dp / gemm::BLOCK_K, l * cb->kp, ws.rowinfo,
+                    cb->cn32 + static_cast<long long>(l) * cb->kp, ws.cand, c.scores, cb->kp));
+                NAT_LAUNCH(2, st, rows::sample_from_acc_kernel<<<std::min((n + 7) / 8, cb->sm_count * 16), 256, 0, st>>>(
+                    ua, sargs, c.scores, cb->kp, cb->cn32 + static_cast<long long>(l) * cb->kp));
+            } else {
+                const size_t smem = scan_smem + static_cast<size_t>(cb->K) * sizeof(float);
+                NAT_LAUNCH(3, st, rows::sample_scan_kernel<<<std::min(n, scan_grid), rows::kScanThreads, smem, st>>>(ua, sargs));
+            }
         } else if (!c.exact && c.temperatures == nullptr) {
             NAT_LAUNCH(1, st, gemm::rvq_gemm_topk_kernel<false><<<std::min(n_tiles, cb->sm_count), gemm::NUM_THREADS,
                                                                    gemm::SMEM_BYTES, st>>>(
@@ -556,6 +567,10 @@ static int encode_impl(const nat_rvq_codebooks* cb_const, const float* x_dev, in
     EncodeCall call{cb, x_dev, layout, T, N, codes_out_dev, code_dtype, quantized_out_dev, loss_out_dev != nullptr,
                     stats_dev, (flags & NAT_RVQ_EXACT_SCAN) != 0};
     call.temperatures = temperatures; call.noise = noise_dev; call.seed = seed; call.draw_base = draw_base;
+    if (temperatures != nullptr && noise_dev == nullptr && !call.exact) {
+        const size_t bytes = static_cast<size_t>(ws[0].rows) * cb->kp * sizeof(float);
+        NAT_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&call.scores), bytes, st));
+    }
     for (int i = 0; i < n_lanes; ++i) {
         NAT_CUDA(cudaMemsetAsync(ws[i].loss_acc, 0, sizeof(double) * cb->L, lane_st[i]));
         if (cb->dp != cb->D) NAT_CUDA(cudaMemsetAsync(ws[i].a, 0, static_cast<size_t>(ws[i].rows) * cb->dp * 2, lane_st[i]));
@@ -572,6 +587,7 @@ static int encode_impl(const nat_rvq_codebooks* cb_const, const float* x_dev, in
             NAT_CUDA(cudaStreamWaitEvent(st, cb->side_ev[1 + i], 0));
         }
     }
+    if (call.scores != nullptr) NAT_CUDA(cudaFreeAsync(call.scores, st));
     if (loss_out_dev != nullptr) {
         NAT_LAUNCH(4, st, rows::finish_loss_kernel<<<1, 32, 0, st>>>(ws[0].loss_acc, two ? ws[1].loss_acc : nullptr, cb->L,
                                                                    static_cast<double>(N) * cb->D, commitment_weight,
@@ -593,7 +609,7 @@ int nat_rvq_sample_f32(const nat_rvq_codebooks* cb, const float* x_dev, int layo
                        void* codes_out_dev, int code_dtype, float* quantized_out_dev, float* loss_out_dev,
                        float commitment_weight, const float* temperatures_host, const float* noise_dev,
                        unsigned long long philox_seed, unsigned long long philox_draw, void* workspace_dev,
-                       size_t workspace_bytes, void* stream) {
+                       size_t workspace_bytes, int flags, void* stream) {
     if (cb == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null codebook handle");
     if (temperatures_host == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null temperature array");
     for (int l = 0; l < cb->L; ++l)
@@ -604,7 +620,8 @@ int nat_rvq_sample_f32(const nat_rvq_codebooks* cb, const float* x_dev, int layo
         return fail(NAT_ERR_UNSUPPORTED, "sampling mode keeps K scores in shared memory: codebook_size %d is too large", cb->K);
     NAT_CUDA(cudaFuncSetAttribute(nat::rows::sample_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     return encode_impl(cb, x_dev, layout, B, T, codes_out_dev, code_dtype, quantized_out_dev, loss_out_dev,
-                       commitment_weight, nullptr, workspace_dev, workspace_bytes, NAT_RVQ_SINGLE_STREAM, stream,
+                       commitment_weight, nullptr, workspace_dev, workspace_bytes,
+                       NAT_RVQ_SINGLE_STREAM | (flags & NAT_RVQ_EXACT_SCAN), stream,
                        temperatures_host, noise_dev, philox_seed, philox_draw);
 }
 

@@ -59,7 +59,8 @@ __device__ __forceinline__ void topk_insert(int v, int (&m)[NCAND]) {
     m[NCAND - 1] = min(m[NCAND - 1], v);
 }
 
-// DUMP=true writes the raw accumulators instead of candidates (validation of the MMA path, tests only).
+// DUMP=true writes the raw accumulators instead of candidates: validation of the MMA path, and the score matrix of the
+// Philox sampling mode (rows::sample_from_acc_kernel).
 // NAT_GEMM_MINBLOCKS = 2 would only cap registers at 168 per thread (shared memory still admits one CTA per SM) so
 // that row kernels of another stream can co-reside; measured slower on B200, default 1.
 template <bool DUMP>
@@ -177,9 +178,10 @@ rvq_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows,
                     tmem_wait_ld();
                     if (DUMP) {
                         if (row < n_rows) {
-                            float* out = dump + row * dump_ld + chunk * BLOCK_N + g * 32;
+                            // one full 128-byte line per thread, as eight 16-byte stores (dump_ld is a multiple of 256)
+                            uint4* out = reinterpret_cast<uint4*>(dump + static_cast<long long>(row) * dump_ld + chunk * BLOCK_N + g * 32);
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) out[j] = __uint_as_float(v[j]);
+                            for (int j = 0; j < 8; ++j) out[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                         }
                     } else {
 #pragma unroll

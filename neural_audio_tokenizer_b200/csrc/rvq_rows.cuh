@@ -607,6 +607,59 @@ sample_scan_kernel(UpdateArgs p, SampleArgs sa) {
     }
 }
 
+// Philox sampling from tensor-core scores: one warp per frame over the raw accumulators the coarse GEMM dumped
+// (acc[row, k] = x_tilde . c_tilde_k, fp16 operands, fp32 accumulate). Distances carry the coarse pass's rounding
+// (~1e-5 relative), which is immaterial for a path whose contract is distributional; the noise is the SAME Philox
+// stream as sample_scan_kernel's (counter: frame, k / 4, draw), so the two paths pick the same code except where the
+// two best values of  -d_k / T - log q_k  nearly tie (tests compare them frame by frame).
+__global__ void __launch_bounds__(256)
+sample_from_acc_kernel(UpdateArgs p, SampleArgs sa, const float* __restrict__ acc, int acc_ld,
+                       const float* __restrict__ cn32) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int dp4 = p.dp >> 2;
+    const float inv_t = 1.f / sa.temperature;
+    for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < p.n; row += warps) {
+        const float4* r4 = reinterpret_cast<const float4*>(p.r + static_cast<long long>(row) * p.dp);
+        double xn = 0.0;
+        for (int i = lane; i < dp4; i += 32) {
+            const float4 v = r4[i];
+            xn += static_cast<double>(v.x) * v.x + static_cast<double>(v.y) * v.y + static_cast<double>(v.z) * v.z +
+                  static_cast<double>(v.w) * v.w;
+        }
+        const float xnf = static_cast<float>(warp_sum(xn));
+        const float alpha = p.rowinfo[row].x;
+        const float4* a4 = reinterpret_cast<const float4*>(acc + static_cast<long long>(row) * acc_ld);
+        const unsigned long long g = sa.row0 + static_cast<unsigned long long>(row);
+        float bv = -__int_as_float(0x7F800000);
+        int bi = 0x7FFFFFFF;
+        for (int k4 = lane; k4 * 4 < p.K; k4 += 32) {           // four consecutive codes per lane: one Philox block
+            const float4 a = a4[k4];
+            const float4 c = __ldg(reinterpret_cast<const float4*>(cn32) + k4);
+            uint32_t ctr[4] = {static_cast<uint32_t>(g), static_cast<uint32_t>(g >> 32), static_cast<uint32_t>(k4), sa.draw};
+            philox4x32_10(ctr, static_cast<uint32_t>(sa.seed), static_cast<uint32_t>(sa.seed >> 32));
+            const float av[4] = {a.x, a.y, a.z, a.w}, cv[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int k = k4 * 4 + e;
+                if (k < p.K) {
+                    const float d = sqrtf(fmaxf(fmaf(av[e], alpha, cv[e]) + xnf, 0.f));
+                    const float v = -d * inv_t - logf(exp1_from_bits(ctr[e]));
+                    if (v > bv) { bv = v; bi = k; }                 // k ascending per lane: first maximum kept
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        bi = min(max(bi, 0), p.K - 1);
+        apply_code(p, row, bi);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------- loss
 // Deterministic fixed-order sum of row_loss[0..n) added to *acc (one block).
 __global__ void __launch_bounds__(1024)

@@ -12,7 +12,8 @@ Contract: the tensor-core path implements the ARGMIN branch (nat.py:2155-2157). 
   * "host_noise" (default): the Exp(1) draws behind `torch.multinomial(probs, 1)` are made on the host from torch's CPU
     generator, in the reference's order, and shipped to the device (nat_rvq_sample_f32) -- seeded runs reproduce the
     reference's codes except at near-ties of probs / q. Meant for the reference's own clip sizes (N*K floats per layer);
-  * "philox": device-side noise, equal to the reference in distribution only (stated, never silent);
+  * "philox": device-side noise, equal to the reference in distribution only (stated, never silent); distances from
+    the tensor-core pass, bulk throughput. "philox_exact" keeps the exact per-frame scan with the same noise;
   * "delegate": call `stochastic_delegate` (e.g. the unmodified reference module).
 Training mode (EMA codebook updates, nat.py:2179-2181) always goes to `stochastic_delegate` or raises. The module
 never returns argmin codes when sampling was asked for. There is no CPU path: tensors must live on a CUDA device.
@@ -160,7 +161,7 @@ def _native_sample(pack: _CodebookPack, codebooks: Sequence[torch.Tensor], x_bct
             if t > 0:
                 host[l].copy_(torch.empty((N, K), dtype=torch.float32).exponential_(1))
         noise = host.to(dev, non_blocking=True)
-    elif mode != "philox":
+    elif mode not in ("philox", "philox_exact"):
         raise ValueError(f"unknown sampling_mode {mode!r}")
     if N == 0:
         if loss is not None:
@@ -176,7 +177,8 @@ def _native_sample(pack: _CodebookPack, codebooks: Sequence[torch.Tensor], x_bct
             quantized.data_ptr() if quantized is not None else None,
             loss.data_ptr() if loss is not None else None, float(commitment_weight), temps,
             noise.data_ptr() if noise is not None else None, int(torch.initial_seed()) & (2 ** 64 - 1),
-            int(philox_draw), ws.data_ptr(), ws_bytes, torch.cuda.current_stream(dev).cuda_stream))
+            int(philox_draw), ws.data_ptr(), ws_bytes, _lib.RVQ_EXACT_SCAN if mode == "philox_exact" else 0,
+            torch.cuda.current_stream(dev).cuda_stream))
     return codes, quantized, loss
 
 
