@@ -208,6 +208,35 @@ __device__ __forceinline__ void load_code(float4 (&cv)[NV], const float4* __rest
         cv[k] = q < dp4 ? __ldcg(c4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
+// 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256): half the memory instructions of the 128-bit forms. The
+// update warps are bound by memory instructions in flight, not by bytes.
+struct F8 { float v[8]; };
+__device__ __forceinline__ F8 ldcg256(const float* p) {
+    F8 r;
+    asm volatile("ld.global.cg.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+                 : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ void stg256(float* p, const F8& r) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]), "f"(r.v[3]), "f"(r.v[4]), "f"(r.v[5]), "f"(r.v[6]), "f"(r.v[7])
+                 : "memory");
+}
+// The same update on a row held as NH groups of eight consecutive floats per lane (group g = floats (g * 32 + lane) * 8 ...).
+template <int NH>
+__device__ __forceinline__ void replay_update8(F8 (&rv)[NH], const float* __restrict__ c, int lane) {
+#pragma unroll
+    for (int g = 0; g < NH; ++g) {
+        const F8 cv = ldcg256(c + (g * 32 + lane) * 8);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float t = __fsub_rn(cv.v[e], rv[g].v[e]);
+            rv[g].v[e] = __fsub_rn(rv[g].v[e], __fadd_rn(rv[g].v[e], t));
+        }
+    }
+}
+
 // r <- r - (r + (c - r)) for one code vector: the reference's update (nat.py:2159, 2167, 1405) on a row held in registers.
 template <int NV>
 __device__ __forceinline__ void replay_update(float4 (&rv)[NV], const float4* __restrict__ c4, int lane) {
@@ -705,8 +734,9 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
                     // ---- phase 1: residual update, next operand, error window
                     const long long tB = w_res.begin();
                     if (!last && loss_l == nullptr && dp4 == NV * 32 && nrows > 0) {
-                        // Hot form: every lane holds exactly NV float4 of a row, nothing is predicated. One row at a
-                        // time per warp; the sixteen update warps of the CTA cover each other's memory latency.
+                        // Hot form: every lane holds exactly NV / 2 groups of eight consecutive floats of a row (256-bit
+                        // loads and stores), nothing is predicated. One row at a time per warp; the sixteen update warps
+                        // of the CTA cover each other's memory latency.
                         // The residual entering the LAST layer is only ever seen through its fp16 operand (the last
                         // layer emits codes and, without a loss, nothing else): it is not written back.
                         const bool keep_r = (store_mask >> l) & 1;
@@ -714,46 +744,48 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, dp]
                         for (int rr = 0; rr < nrows; ++rr) {
                             const int row = row0 + rr;
                             const int j = __shfl_sync(0xffffffffu, jsel, rr);
-                            float4* r4 = reinterpret_cast<float4*>(p.r + static_cast<long long>(row) * p.dp);
-                            const float4* c4 = reinterpret_cast<const float4*>(cb_l + static_cast<long long>(j) * p.dp);
-                            float4 cur[NV], cv[NV];
+                            constexpr int NH = NV / 2;                 // groups of eight floats per lane
+                            float* rrow = p.r + static_cast<long long>(row) * p.dp;
+                            const float* crow = cb_l + static_cast<long long>(j) * p.dp;
+                            F8 cur[NH], cv[NH];
 #pragma unroll
-                            for (int k = 0; k < NV; ++k) cur[k] = __ldcg(r4 + k * 32 + lane);
+                            for (int g = 0; g < NH; ++g) cur[g] = ldcg256(rrow + (g * 32 + lane) * 8);
 #pragma unroll 1
                             for (int back = n_replay; back > 0; --back) {
                                 const int jp = rows::load_code(codes_l, p.code_dtype, code_base - back * p.codes_ld + row);
-                                replay_update<NV>(cur, reinterpret_cast<const float4*>(
-                                    cb_l + (static_cast<long long>(jp) - static_cast<long long>(back) * p.K) * p.dp), lane);
+                                replay_update8<NH>(cur, cb_l + (static_cast<long long>(jp) - static_cast<long long>(back) * p.K) * p.dp, lane);
                             }
 #pragma unroll
-                            for (int k = 0; k < NV; ++k) cv[k] = __ldcg(c4 + k * 32 + lane);
+                            for (int g = 0; g < NH; ++g) cv[g] = ldcg256(crow + (g * 32 + lane) * 8);
                             // operand scale from the bound  max|r'| <= max|r| + max|c|
                             const float bound = (__shfl_sync(0xffffffffu, am_old, rr) + cabs) * 1.00001f;
                             const float sx = rows::pow2_scale_for(bound);
                             const float2 sx2 = make_float2(sx, sx);
-                            uint2* a_row = reinterpret_cast<uint2*>(p.a + static_cast<long long>(row) * p.dp);
+                            uint4* a_row = reinterpret_cast<uint4*>(p.a + static_cast<long long>(row) * p.dp);
                             float2 lo2v = make_float2(0.f, 0.f), xh2v = make_float2(0.f, 0.f);
                             float amax = 0.f;
 #pragma unroll
-                            for (int k = 0; k < NV; ++k) {
+                            for (int g = 0; g < NH; ++g) {
                                 // q = codebook[j]; t = q - r; q_ste = r + t; r' = r - q_ste   (nat.py:2159, 2167, 1405)
-                                const float2 x01 = make_float2(cur[k].x, cur[k].y), x23 = make_float2(cur[k].z, cur[k].w);
-                                const float2 c01 = make_float2(cv[k].x, cv[k].y), c23 = make_float2(cv[k].z, cv[k].w);
-                                const float2 t01 = sub2(c01, x01), t23 = sub2(c23, x23);
-                                const float2 n01 = sub2(x01, __fadd2_rn(x01, t01)), n23 = sub2(x23, __fadd2_rn(x23, t23));
-                                if (keep_r) r4[k * 32 + lane] = make_float4(n01.x, n01.y, n23.x, n23.y);
-                                amax = fmaxf(fmaxf(amax, fabsf(n01.x)), fmaxf(fabsf(n01.y), fmaxf(fabsf(n23.x), fabsf(n23.y))));
-                                const float2 s01 = __fmul2_rn(n01, sx2), s23 = __fmul2_rn(n23, sx2);
-                                const __half2 h01 = __float22half2_rn(s01), h23 = __float22half2_rn(s23);
-                                const float2 l01 = sub2(s01, __half22float2(h01)), l23 = sub2(s23, __half22float2(h23));
-                                lo2v = __ffma2_rn(l01, l01, lo2v);
-                                lo2v = __ffma2_rn(l23, l23, lo2v);
-                                xh2v = __ffma2_rn(s01, s01, xh2v);
-                                xh2v = __ffma2_rn(s23, s23, xh2v);
-                                uint2 packed;
-                                packed.x = *reinterpret_cast<const uint32_t*>(&h01);
-                                packed.y = *reinterpret_cast<const uint32_t*>(&h23);
-                                a_row[k * 32 + lane] = packed;
+                                F8 nr;
+                                uint32_t hp[4];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 x2 = make_float2(cur[g].v[2 * e], cur[g].v[2 * e + 1]);
+                                    const float2 c2 = make_float2(cv[g].v[2 * e], cv[g].v[2 * e + 1]);
+                                    const float2 t2 = sub2(c2, x2);
+                                    const float2 n2 = sub2(x2, __fadd2_rn(x2, t2));
+                                    nr.v[2 * e] = n2.x; nr.v[2 * e + 1] = n2.y;
+                                    amax = fmaxf(amax, fmaxf(fabsf(n2.x), fabsf(n2.y)));
+                                    const float2 s2 = __fmul2_rn(n2, sx2);
+                                    const __half2 h2 = __float22half2_rn(s2);
+                                    const float2 l2 = sub2(s2, __half22float2(h2));
+                                    lo2v = __ffma2_rn(l2, l2, lo2v);
+                                    xh2v = __ffma2_rn(s2, s2, xh2v);
+                                    hp[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                                }
+                                if (keep_r) stg256(rrow + (g * 32 + lane) * 8, nr);
+                                a_row[g * 32 + lane] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
                             }
                             const float lo2 = warp_sum(lo2v.x + lo2v.y), xh2 = warp_sum(xh2v.x + xh2v.y), amx = warp_max(amax);
                             if (lane == 0) {
