@@ -205,6 +205,7 @@ struct nat_rvq_codebooks {
     int* scratch;                     // [L, kScratchPerLayer]
     CUtensorMap map_b;                // box 64 x 256 codes
     CUtensorMap map_b_half;           // box 64 x 128 codes: the half of a B tile one CTA of a pair stages
+    bool pair_ok;                     // the device can co-schedule the two-CTA clusters of the fused kernel
     unsigned long long* stack_dbg;    // [sm_count][DBG_SLOTS] cycle counters of the last fused launch (debug hook)
     bool stack_dbg_on;
     // staging arena of the host-buffer entry point (grown on first use)
@@ -297,6 +298,25 @@ int nat_rvq_codebooks_create(const float* const* codebooks_dev, int L, int K, in
         guard(stack_kernel_attrs<4>(), "cudaFuncSetAttribute");
         guard(stack_kernel_attrs<6>(), "cudaFuncSetAttribute");
         guard(stack_kernel_attrs<8>(), "cudaFuncSetAttribute");
+        {   // CTA pairs need two co-resident CTAs of 768 threads / 224 KB in one cluster (a TPC); ask the runtime
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof cfg);
+            cfg.gridDim = dim3(2, 1, 1);
+            cfg.blockDim = dim3(nat::stack::NUM_THREADS, 1, 1);
+            cfg.dynamicSmemBytes = nat::stack::SMEM_BYTES;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            int clusters = 0;
+            const cudaError_t qe = cudaOccupancyMaxActiveClusters(&clusters, nat::stack::rvq_stack_kernel<6, 2, false>, &cfg);
+            (void)cudaGetLastError();
+            cb->pair_ok = !(qe == cudaSuccess && clusters == 0);      // only a definite "no cluster fits" turns pairs off
+            if (getenv("NAT_B200_VERBOSE"))
+                fprintf(stderr, "nat_b200: cluster occupancy query: %s, %d active clusters -> pairs %s\n",
+                        cudaGetErrorString(qe), clusters, cb->pair_ok ? "on" : "off");
+        }
         guard(cudaFuncSetAttribute(nat::rows::prep_bct_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    200 * 1024), "cudaFuncSetAttribute");
     }
@@ -419,7 +439,7 @@ static int encode_chunk(const EncodeCall& c, const Workspace& ws, const CUtensor
         { const char* e = getenv("NAT_RVQ_STORE_MASK"); if (e) sa.store_mask &= atoi(e); }
         // CTA pairs (one tcgen05.mma.cta_group::2 per two SMs) once there is more than one tile; NAT_RVQ_PAIR=1 keeps
         // the single-CTA form for A/B measurements.
-        const int pair = (n_tiles >= 2 && cb->sm_count >= 2 && fused_pair()) ? 2 : 1;
+        const int pair = (n_tiles >= 2 && cb->sm_count >= 2 && cb->pair_ok && fused_pair()) ? 2 : 1;
         const int grid = pair == 2 ? std::min((n_tiles + 1) & ~1, cb->sm_count & ~1) : std::min(n_tiles, cb->sm_count);
         const CUtensorMap& map_b = pair == 2 ? cb->map_b_half : cb->map_b;
         sa.group = fused_group(pair);
