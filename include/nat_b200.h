@@ -62,7 +62,7 @@ int nat_abi_version(void);
 int nat_device_info(int* sm_count, int* cc_major, int* cc_minor, char* name, size_t name_len);
 
 /* ---------------------------------------------------------------------------------------------------------------
- * Residual vector quantiser (argmin contract)
+ * Residual vector quantiser (argmin contract; the sampling form follows below)
  * Replaces: ResidualVectorQuantizer.forward / .encode (nat.py:1358-1426) and the VectorQuantizer.forward it loops
  * over (nat.py:2119-2183), argmin branch (nat.py:2155-2157).
  * ------------------------------------------------------------------------------------------------------------- */

@@ -7,22 +7,24 @@
 // only cross-layer dependency (tile t of layer l+1 needs the update of tile t of layer l) stays inside the CTA and
 // is a shared-memory counter, not a grid-wide barrier or a kernel boundary.
 //
-// Order of work inside a CTA: its tiles are taken in groups of `group` tiles; inside a group the jobs run
-// layer-major  (t0,l0) (t1,l0) (t0,l1) (t1,l1) ...  so the update of one tile runs under the GEMM of the other(s)
-// and a tile's residual / operand rows are re-read a few microseconds after they were written, from L2.
+// Order of work inside a CTA: its tiles are taken in groups of `group` tiles (3 by default); inside a group the jobs
+// run layer-major  (t0,l0) (t1,l0) (t2,l0) (t0,l1) ...  so the update of one tile runs under the GEMMs of the others.
+// The live residual / operand rows of all CTAs together exceed L2, so they travel through HBM between layers; the
+// write-back policy (`store_mask`) keeps that traffic to one residual write per four-layer stack.
 //
-// Warp roles (448 threads):
+// Warp roles (768 threads, launched as clusters of two CTAs: see the kernel's comment):
 //   warps 0..3    candidates: tcgen05.ld of the accumulators, coarse score, running-threshold candidate list
-//   warps 4..11   update: exact decision (fp64 re-rank where the window demands it), residual update in the
+//   warps 4..19   update: exact decision (fp64 re-rank where the window demands it), residual update in the
 //                 reference's op order, next-layer fp16 operand + error window, index streams
-//   warp 12       TMA producer (A tile 128 frames x 64, B tile 256 codes x 64 per K-block, 4-stage ring)
-//   warp 13       TMEM owner + single-thread tcgen05.mma issuer (two 256-column accumulator stages)
+//   warp 20       TMA producer (A tile 128 frames x 64, B tile 256 / PAIR codes x 64 per K-block, 4- or 6-stage ring)
+//   warp 21       TMEM owner + single-thread tcgen05.mma issuer (two 256-column accumulator stages)
+//   warps 22, 23  idle (they complete the sixth warpgroup that setmaxnreg needs)
 //
 // Coarse pass and certificate (DESIGN.md "Exactness"): for frame n the kept set is every code whose coarse score
 // s_k = acc_k * alpha + ||c_k||^2 lies within the frame's proven window W of the running minimum; the final filter
 // against the final minimum leaves {k : s_k <= min_k s + W}, which must contain the true fp32-data argmin. One
-// survivor: certified. Several: exact fp64 re-rank. List overflow (adversarial orderings only): exact full scan by
-// the update warp. Ties go to the lowest index (nat.py:2157).
+// survivor: certified. Several (up to 15 travel in the hand-off record): exact fp64 re-rank. More, or list overflow
+// (adversarial orderings only): exact full scan by the update warp. Ties go to the lowest index (nat.py:2157).
 #pragma once
 
 #include "nat_common.cuh"
