@@ -418,9 +418,10 @@ static int encode_chunk(const EncodeCall& c, const Workspace& ws, const CUtensor
     const int cbytes = code_bytes(c.code_dtype);
     const long long cb_layer_ld = static_cast<long long>(cb->K) * cb->dp;
     if (int rc = launch_layer0_prep(cb, ws, c.x, c.layout, c.T, n0, n, st)) return rc;
-    NAT_CUDA(cudaMemsetAsync(ws.scan_count, 0, sizeof(int) * cb->L, st));
     const int n_tiles = (n + gemm::BLOCK_M - 1) / gemm::BLOCK_M;
-    if (!c.exact && c.temperatures == nullptr && fused_enabled() && cb->dp <= 1024) {
+    const bool fused = !c.exact && c.temperatures == nullptr && fused_enabled() && cb->dp <= 1024;
+    if (!fused) NAT_CUDA(cudaMemsetAsync(ws.scan_count, 0, sizeof(int) * cb->L, st));   // only the per-layer kernels list scans
+    if (fused) {
         // one persistent launch for all L layers (rvq_stack_sm100.cuh)
         stack::StackArgs sa;
         sa.cbf = cb->cbf; sa.cn64 = cb->cn64; sa.cn32 = cb->cn32; sa.lc = cb->lc;
@@ -592,7 +593,7 @@ static int encode_impl(const nat_rvq_codebooks* cb_const, const float* x_dev, in
         NAT_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&call.scores), bytes, st));
     }
     for (int i = 0; i < n_lanes; ++i) {
-        NAT_CUDA(cudaMemsetAsync(ws[i].loss_acc, 0, sizeof(double) * cb->L, lane_st[i]));
+        if (loss_out_dev != nullptr) NAT_CUDA(cudaMemsetAsync(ws[i].loss_acc, 0, sizeof(double) * cb->L, lane_st[i]));
         if (cb->dp != cb->D) NAT_CUDA(cudaMemsetAsync(ws[i].a, 0, static_cast<size_t>(ws[i].rows) * cb->dp * 2, lane_st[i]));
     }
     int lane = 0;
