@@ -134,7 +134,9 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank)
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    // default semantics (.release at CTA scope), as CUTLASS's ClusterBarrier::arrive(cta_id): the barrier hands over
+    // TMEM / shared-memory stages, never generic-proxy data of another CTA, and a cluster-scope release costs a fence
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // Load into THIS CTA's shared memory, completion bytes counted on a barrier that may live in the peer CTA.
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr,
