@@ -353,12 +353,20 @@ int nat_rvq_codebooks_dims(const nat_rvq_codebooks* cb, int* L, int* K, int* D) 
     return NAT_OK;
 }
 
+// Inputs whose tiles x codebook chunks fit one wave of SMs take the split-GEMM + row-argmin path (low latency); its
+// score matrix [rows, kp] fp32 sits at the tail of the caller's workspace.
+static size_t small_input_scores_bytes(const nat_rvq_codebooks* cb, long long n_frames) {
+    const long long tiles = (n_frames + 127) / 128;
+    if (tiles * (cb->kp / nat::gemm::BLOCK_N) > cb->sm_count) return 0;
+    return static_cast<size_t>(tiles) * 128 * cb->kp * sizeof(float);
+}
+
 size_t nat_rvq_workspace_bytes(const nat_rvq_codebooks* cb, int64_t n_frames) {
     if (cb == nullptr || n_frames <= 0) return kWsFixed + 256 * 9 + 128 * ws_per_row(64, 16);
     // two lanes, each holding half of the frames rounded up to a tile (see nat_rvq_encode_f32)
     const long long per_lane = std::min<long long>(round_up((n_frames + 1) / 2, 128), chunk_cap_rows() / 2);
     const size_t lane_bytes = static_cast<size_t>(round_up(kWsFixed + 256 * 9 + per_lane * ws_per_row(cb->dp, cb->L), 256));
-    return 2 * lane_bytes;
+    return 2 * lane_bytes + small_input_scores_bytes(cb, n_frames);
 }
 
 // ------------------------------------------------------------------------------------------------- encode
@@ -387,6 +395,10 @@ static int launch_layer0_prep(const nat_rvq_codebooks* cb, const Workspace& ws, 
 
 static bool fused_enabled() {
     const char* e = getenv("NAT_RVQ_FUSED");         // read every call: tests flip it to cross-check both paths
+    return e == nullptr || atoi(e) != 0;
+}
+static bool small_path_enabled() {
+    const char* e = getenv("NAT_RVQ_SMALL");           // read every call: tests flip it to cover the fused kernel on small inputs
     return e == nullptr || atoi(e) != 0;
 }
 static bool fused_pair() {
@@ -419,7 +431,7 @@ static int encode_chunk(const EncodeCall& c, const Workspace& ws, const CUtensor
     const long long cb_layer_ld = static_cast<long long>(cb->K) * cb->dp;
     if (int rc = launch_layer0_prep(cb, ws, c.x, c.layout, c.T, n0, n, st)) return rc;
     const int n_tiles = (n + gemm::BLOCK_M - 1) / gemm::BLOCK_M;
-    const bool fused = !c.exact && c.temperatures == nullptr && fused_enabled() && cb->dp <= 1024;
+    const bool fused = !c.exact && c.temperatures == nullptr && fused_enabled() && cb->dp <= 1024 && c.scores == nullptr;
     if (!fused) NAT_CUDA(cudaMemsetAsync(ws.scan_count, 0, sizeof(int) * cb->L, st));   // only the per-layer kernels list scans
     if (fused) {
         // one persistent launch for all L layers (rvq_stack_sm100.cuh)
@@ -483,7 +495,7 @@ static int encode_chunk(const EncodeCall& c, const Workspace& ws, const CUtensor
                 // Philox noise: distances from the tensor-core pass (score matrix through HBM), one warp per frame
                 NAT_LAUNCH(1, st, gemm::rvq_gemm_topk_kernel<true><<<std::min(n_tiles, cb->sm_count), gemm::NUM_THREADS,
                                                                   gemm::SMEM_BYTES, st>>>(
-                    map_a, cb->map_b, n, n_tiles, cb->kp / gemm::BLOCK_N, cb->dp / gemm::BLOCK_K, l * cb->kp, ws.rowinfo,
+                    map_a, cb->map_b, n, n_tiles, cb->kp / gemm::BLOCK_N, cb->dp / gemm::BLOCK_K, l * cb->kp, 1, ws.rowinfo,
                     cb->cn32 + static_cast<long long>(l) * cb->kp, ws.cand, c.scores, cb->kp));
                 NAT_LAUNCH(2, st, rows::sample_from_acc_kernel<<<std::min((n + 7) / 8, cb->sm_count * 16), 256, 0, st>>>(
                     ua, sargs, c.scores, cb->kp, cb->cn32 + static_cast<long long>(l) * cb->kp));
@@ -491,10 +503,19 @@ static int encode_chunk(const EncodeCall& c, const Workspace& ws, const CUtensor
                 const size_t smem = scan_smem + static_cast<size_t>(cb->K) * sizeof(float);
                 NAT_LAUNCH(3, st, rows::sample_scan_kernel<<<std::min(n, scan_grid), rows::kScanThreads, smem, st>>>(ua, sargs));
             }
+        } else if (!c.exact && c.temperatures == nullptr && c.scores != nullptr) {
+            // few tiles: the coarse GEMM dealt over tiles x codebook chunks, then one warp per frame (low latency)
+            const int n_chunks = cb->kp / gemm::BLOCK_N;
+            NAT_LAUNCH(1, st, gemm::rvq_gemm_topk_kernel<true><<<std::min(n_tiles * n_chunks, cb->sm_count), gemm::NUM_THREADS,
+                                                              gemm::SMEM_BYTES, st>>>(
+                map_a, cb->map_b, n, n_tiles, n_chunks, cb->dp / gemm::BLOCK_K, l * cb->kp, n_chunks, ws.rowinfo,
+                cb->cn32 + static_cast<long long>(l) * cb->kp, ws.cand, c.scores, cb->kp));
+            NAT_LAUNCH(2, st, rows::argmin_from_acc_kernel<<<std::min((n + 7) / 8, cb->sm_count * 16), 256, 0, st>>>(
+                ua, c.scores, cb->kp, cb->cn32 + static_cast<long long>(l) * cb->kp));
         } else if (!c.exact && c.temperatures == nullptr) {
             NAT_LAUNCH(1, st, gemm::rvq_gemm_topk_kernel<false><<<std::min(n_tiles, cb->sm_count), gemm::NUM_THREADS,
                                                                    gemm::SMEM_BYTES, st>>>(
-                map_a, cb->map_b, n, n_tiles, cb->kp / gemm::BLOCK_N, cb->dp / gemm::BLOCK_K, l * cb->kp, ws.rowinfo,
+                map_a, cb->map_b, n, n_tiles, cb->kp / gemm::BLOCK_N, cb->dp / gemm::BLOCK_K, l * cb->kp, 1, ws.rowinfo,
                 cb->cn32 + static_cast<long long>(l) * cb->kp, ws.cand, nullptr, 0));
             NAT_LAUNCH(2, st, rows::decide_update_kernel<<<std::min((n + 7) / 8, cb->sm_count * 16), 256, 0, st>>>(
                 ua, ws.cand, ws.scan_list, ws.scan_count + l));
@@ -561,6 +582,15 @@ static int encode_impl(const nat_rvq_codebooks* cb_const, const float* x_dev, in
     // Two halves of the workspace on two internal streams: the HBM-bound row kernels of one half run under the
     // tensor-bound GEMM of the other. Small inputs (or NAT_RVQ_SINGLE_STREAM / NAT_RVQ_STREAMS=1) stay on `st`.
     const bool two = overlap_enabled() && !(flags & NAT_RVQ_SINGLE_STREAM) && N >= 4LL * 128 * cb->sm_count;
+    // small-input path: its score matrix is carved off the tail of the workspace (when the caller sized it with
+    // nat_rvq_workspace_bytes for this many frames; a smaller workspace simply keeps the fused kernel)
+    size_t scores_bytes = (temperatures == nullptr && !(flags & NAT_RVQ_EXACT_SCAN) && small_path_enabled() && !two)
+                              ? small_input_scores_bytes(cb, N) : 0;
+    if (scores_bytes != 0) {
+        const size_t main_bytes = static_cast<size_t>(round_up(kWsFixed + 256 * 9 + round_up(N, 128) * ws_per_row(cb->dp, cb->L), 256));
+        if (workspace_bytes < main_bytes + scores_bytes + 256) scores_bytes = 0;
+        else workspace_bytes = (workspace_bytes - scores_bytes) & ~static_cast<size_t>(255);
+    }
     const int n_lanes = two ? 2 : 1;
     Workspace ws[2];
     CUtensorMap map_a[2];
@@ -588,9 +618,15 @@ static int encode_impl(const nat_rvq_codebooks* cb_const, const float* x_dev, in
     EncodeCall call{cb, x_dev, layout, T, N, codes_out_dev, code_dtype, quantized_out_dev, loss_out_dev != nullptr,
                     stats_dev, (flags & NAT_RVQ_EXACT_SCAN) != 0};
     call.temperatures = temperatures; call.noise = noise_dev; call.seed = seed; call.draw_base = draw_base;
-    if (temperatures != nullptr && noise_dev == nullptr && !call.exact) {
+    // Score matrix (accumulator dump): the Philox sampling path, and the small-input argmin path -- inputs whose
+    // tiles x codebook chunks fit one wave of SMs would otherwise run a whole stack on a few persistent CTAs.
+    bool scores_owned = false;
+    if (scores_bytes != 0) {
+        call.scores = reinterpret_cast<float*>(static_cast<char*>(workspace_dev) + workspace_bytes);   // the tail cut off above
+    } else if (temperatures != nullptr && noise_dev == nullptr && !call.exact) {
         const size_t bytes = static_cast<size_t>(ws[0].rows) * cb->kp * sizeof(float);
         NAT_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&call.scores), bytes, st));
+        scores_owned = true;
     }
     for (int i = 0; i < n_lanes; ++i) {
         if (loss_out_dev != nullptr) NAT_CUDA(cudaMemsetAsync(ws[i].loss_acc, 0, sizeof(double) * cb->L, lane_st[i]));
@@ -608,7 +644,7 @@ static int encode_impl(const nat_rvq_codebooks* cb_const, const float* x_dev, in
             NAT_CUDA(cudaStreamWaitEvent(st, cb->side_ev[1 + i], 0));
         }
     }
-    if (call.scores != nullptr) NAT_CUDA(cudaFreeAsync(call.scores, st));
+    if (scores_owned) NAT_CUDA(cudaFreeAsync(call.scores, st));
     if (loss_out_dev != nullptr) {
         NAT_LAUNCH(4, st, rows::finish_loss_kernel<<<1, 32, 0, st>>>(ws[0].loss_acc, two ? ws[1].loss_acc : nullptr, cb->L,
                                                                    static_cast<double>(N) * cb->D, commitment_weight,
@@ -773,7 +809,7 @@ int nat_debug_rvq_scores(const nat_rvq_codebooks* cb, int layer, const float* ro
         rows_dev, cb->D, n, cb->D, cb->dp, ws.r, ws.a, ws.rowinfo, ws.rowamax, cb->lc + layer, false));
     const int n_tiles = (n + gemm::BLOCK_M - 1) / gemm::BLOCK_M;
     NAT_LAUNCH(1, st, gemm::rvq_gemm_topk_kernel<true><<<std::min(n_tiles, cb->sm_count), gemm::NUM_THREADS, gemm::SMEM_BYTES, st>>>(
-        map_a, cb->map_b, n, n_tiles, cb->kp / gemm::BLOCK_N, cb->dp / gemm::BLOCK_K, layer * cb->kp, ws.rowinfo,
+        map_a, cb->map_b, n, n_tiles, cb->kp / gemm::BLOCK_N, cb->dp / gemm::BLOCK_K, layer * cb->kp, 1, ws.rowinfo,
         cb->cn32 + static_cast<long long>(layer) * cb->kp, ws.cand, scores_out_dev, cb->kp));
     NAT_CUDA(cudaGetLastError());
     if (row_scale_out_dev)

@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(NUM_THREADS, NAT_GEMM_MINBLOCKS)
 rvq_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows, Dp], box 64 x 128, SWIZZLE_128B
                      const __grid_constant__ CUtensorMap map_b,   // fp16 [L*Kp, Dp], box 64 x 256, SWIZZLE_128B
                      int n_rows, int n_tiles, int n_chunks, int n_kblocks, int b_row0,
+                     int n_splits,                                // DUMP only: a tile's chunks are dealt to n_splits CTAs
                      const float4* __restrict__ rowinfo,          // per frame {alpha, bias, window, -}
                      const float* __restrict__ cn,                // [Kp] ||c_k||^2 of this layer, +inf in the padding
                      Cand* __restrict__ cand, float* __restrict__ dump, int dump_ld) {
@@ -84,6 +85,9 @@ rvq_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows,
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    if (!DUMP) n_splits = 1;                                      // candidate lists are merged across a tile's chunks
+    n_splits = max(1, min(n_splits, n_chunks));
+    const int cps = (n_chunks + n_splits - 1) / n_splits;        // chunks per work item
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
@@ -103,8 +107,9 @@ rvq_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows,
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             uint32_t s = 0, ph = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                for (int chunk = 0; chunk < n_chunks; ++chunk) {
+            for (int w = blockIdx.x; w < n_tiles * n_splits; w += gridDim.x) {
+                const int tile = w / n_splits, c0 = (w % n_splits) * cps, c1 = min(n_chunks, c0 + cps);
+                for (int chunk = c0; chunk < c1; ++chunk) {
                     for (int kb = 0; kb < n_kblocks; ++kb) {
                         mbar_wait(&empty[s], ph ^ 1);
                         mbar_arrive_expect_tx(&full[s], A_STAGE_BYTES + B_STAGE_BYTES);
@@ -122,8 +127,9 @@ rvq_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows,
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_f16_f32(BLOCK_M, BLOCK_N);
             uint32_t s = 0, ph = 0, it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                for (int chunk = 0; chunk < n_chunks; ++chunk, ++it) {
+            for (int w = blockIdx.x; w < n_tiles * n_splits; w += gridDim.x) {
+                const int c0 = (w % n_splits) * cps, c1 = min(n_chunks, c0 + cps);
+                for (int chunk = c0; chunk < c1; ++chunk, ++it) {
                     const uint32_t as = it & 1, aph = (it >> 1) & 1;
                     mbar_wait(&tempty[as], aph ^ 1);
                     tcgen05_fence_after();
@@ -151,7 +157,8 @@ rvq_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows,
         const int q = warp & 3;                       // TMEM lane quarter this warp may touch
         const int row_in_tile = q * 32 + lane;
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int w = blockIdx.x; w < n_tiles * n_splits; w += gridDim.x) {
+            const int tile = w / n_splits, c0 = (w % n_splits) * cps, c1 = min(n_chunks, c0 + cps);
             const long long row = static_cast<long long>(tile) * BLOCK_M + row_in_tile;
             float alpha = 0.f, bias = 0.f;
             if (row < n_rows) {
@@ -162,7 +169,7 @@ rvq_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows,
             int gk[NCAND], gi[NCAND];
 #pragma unroll
             for (int i = 0; i < NCAND; ++i) { gk[i] = KEY_INVALID; gi[i] = 0; }
-            for (int chunk = 0; chunk < n_chunks; ++chunk, ++it) {
+            for (int chunk = c0; chunk < c1; ++chunk, ++it) {
                 const uint32_t as = it & 1, aph = (it >> 1) & 1;
                 mbar_wait(&tfull[as], aph);
                 tcgen05_fence_after();

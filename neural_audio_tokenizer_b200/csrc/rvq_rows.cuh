@@ -660,6 +660,81 @@ sample_from_acc_kernel(UpdateArgs p, SampleArgs sa, const float* __restrict__ ac
     }
 }
 
+// ---------------------------------------------------------------------------------------------------- small inputs
+// Exact argmin from a dumped accumulator matrix: the low-latency form for inputs of a few tiles, where the persistent
+// fused kernel would run a whole stack on a handful of SMs. The coarse GEMM is dealt over tiles x codebook chunks
+// (rvq_gemm_topk_kernel<DUMP>, n_splits) and this kernel, one warp per frame, applies the same certificate as the
+// fused kernel to the same coarse scores  s_k = fma(acc_k, alpha, ||c_k||^2): every code within the frame's proven
+// window of the minimum is a candidate; one candidate is certified, several are re-ranked exactly in fp64
+// (ties -> lowest index), then the code is applied (residual update, next operand).
+__global__ void __launch_bounds__(256)
+argmin_from_acc_kernel(UpdateArgs p, const float* __restrict__ acc, int acc_ld, const float* __restrict__ cn32) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int dp4 = p.dp >> 2;
+    const int k4n = (p.K + 3) >> 2;
+    unsigned long long n_cert = 0, n_rerank = 0;
+    for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < p.n; row += warps) {
+        const float4 ri = p.rowinfo[row];
+        const float alpha = ri.x, window = ri.z;
+        const float4* a4 = reinterpret_cast<const float4*>(acc + static_cast<long long>(row) * acc_ld);
+        const float4* c4n = reinterpret_cast<const float4*>(cn32);
+        const float inf = __int_as_float(0x7F800000);
+        float m = inf;
+        for (int k4 = lane; k4 < k4n; k4 += 32) {              // padding columns carry ||c||^2 = +inf
+            const float4 a = a4[k4];
+            const float4 c = __ldg(c4n + k4);
+            m = fminf(fminf(m, fminf(fmaf(a.x, alpha, c.x), fmaf(a.y, alpha, c.y))),
+                      fminf(fmaf(a.z, alpha, c.z), fmaf(a.w, alpha, c.w)));
+        }
+        m = -warp_max(-m);
+        const float thr = fmaf(fabsf(m) + window, 2.4e-7f, m + window);     // m + W rounded up (superset of the window)
+        const float4* r4 = reinterpret_cast<const float4*>(p.r + static_cast<long long>(row) * p.dp);
+        double best = 0.0;
+        int bestj = -1, n_cand = 0, only = 0;
+        for (int k40 = 0; k40 < k4n; k40 += 32) {
+            const int k4 = k40 + lane;
+            float sc[4] = {inf, inf, inf, inf};
+            if (k4 < k4n) {
+                const float4 a = a4[k4];
+                const float4 c = __ldg(c4n + k4);
+                sc[0] = fmaf(a.x, alpha, c.x); sc[1] = fmaf(a.y, alpha, c.y);
+                sc[2] = fmaf(a.z, alpha, c.z); sc[3] = fmaf(a.w, alpha, c.w);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                unsigned hits = __ballot_sync(0xffffffffu, sc[e] <= thr && k4 * 4 + e < p.K);
+                while (hits != 0) {                               // warp-uniform
+                    const int src = __ffs(hits) - 1;
+                    hits &= hits - 1;
+                    const int k = (k40 + src) * 4 + e;
+                    if (n_cand == 0) {
+                        only = k;                                 // scored only if a second candidate turns up
+                    } else {
+                        if (n_cand == 1) {
+                            best = exact_score(r4, reinterpret_cast<const float4*>(p.cb + static_cast<long long>(only) * p.dp),
+                                               dp4, p.cn64[only]);
+                            bestj = only;
+                        }
+                        const double s = exact_score(r4, reinterpret_cast<const float4*>(p.cb + static_cast<long long>(k) * p.dp),
+                                                     dp4, p.cn64[k]);
+                        if (s < best || (s == best && k < bestj)) { best = s; bestj = k; }
+                    }
+                    ++n_cand;
+                }
+            }
+        }
+        int j = n_cand <= 1 ? only : bestj;
+        if (n_cand == 0) j = 0;                                   // cannot happen for finite input (the minimum is a hit)
+        if (n_cand <= 1) ++n_cert; else ++n_rerank;
+        apply_code(p, row, j);
+    }
+    if (p.stats != nullptr && lane == 0) {
+        if (n_cert) atomicAdd(p.stats + 0, n_cert);
+        if (n_rerank) atomicAdd(p.stats + 1, n_rerank);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------- loss
 // Deterministic fixed-order sum of row_loss[0..n) added to *acc (one block).
 __global__ void __launch_bounds__(1024)

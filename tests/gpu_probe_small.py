@@ -10,7 +10,7 @@ D, K = 768, 1024
 rvq = ResidualVectorQuantizer(D, K, 4, use_stochastic=False).eval().cuda()
 h = rvq._pack.get(rvq._codebooks())
 st = torch.cuda.current_stream().cuda_stream
-for N in (75, 1000):
+for N in (75, 1000, 4000, 4736):
     x = torch.randn(1, D, N, device="cuda")
     wsb = lib.nat_rvq_workspace_bytes(h, N); ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
     codes = torch.empty((4, N), dtype=torch.int16, device="cuda")

@@ -10,6 +10,14 @@ from oracle import rvq_oracle
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(params=["small_input_path", "fused_kernel_only"], autouse=True)
+def _dispatch(request, monkeypatch):
+    """Inputs of a few tiles take the split-GEMM + row-argmin path by default; every test here also runs with that path
+    switched off, so that the persistent fused kernel is exercised on the small golden cases as well."""
+    monkeypatch.setenv("NAT_RVQ_SMALL", "1" if request.param == "small_input_path" else "0")
+    yield
+
 RVQ_CASES = ["rvq_small", "rvq_ragged", "rvq_ties", "rvq_single_frame", "rvq_768x1024", "rvq_512x4096",
              "rvq_1024x1024"]
 
