@@ -386,3 +386,30 @@ def test_random_shapes_tensor_path_equals_exact_scan():
         enc = fast.encode(x)                                 # codes-only form takes the hot update path
         for u, v in zip(enc, cb_):
             assert torch.equal(u, v), (trial, D, K, L, N, "encode")
+
+
+def test_chunk_path_is_cuda_graph_capturable():
+    """BASELINE config 5 (1 s chunks): encode() issues only stream-ordered work on the current stream, so the chunk
+    path can be captured once and replayed; replays follow new input and equal the eager codes."""
+    torch.manual_seed(21)
+    cbs = torch.randn(4, 1024, 768)
+    rvq = _dropin(cbs)
+    x = torch.randn(1, 768, 75, device="cuda")
+    eager = [c.clone() for c in rvq.encode(x)]                # also builds the codebook handle outside the capture
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            rvq.encode(x)
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = rvq.encode(x)
+    g.replay()
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, b) for a, b in zip(eager, out))
+    x.copy_(torch.randn(1, 768, 75, device="cuda"))
+    g.replay()
+    torch.cuda.synchronize()
+    fresh = rvq.encode(x)
+    assert all(torch.equal(a, b) for a, b in zip(fresh, out))
