@@ -59,7 +59,10 @@ constexpr int LAUNCH_REGS = (65536 / NUM_THREADS) / 8 * 8;     // registers per 
 // 80 registers per thread at launch (768 threads); after setmaxnreg: 128 * (88 + 4 * 88 + 40) <= 64 K.
 // NAT_UPD_WARPS / NAT_REGS_* are A/B build knobs: 8 update warps with 120 registers measured 12 % slower than 16 with 88
 // (the update is bound by rows in flight, not by registers).
-constexpr int REGS_EPI = NAT_REGS_EPI, REGS_UPD = NAT_REGS_UPD, REGS_AUX = 40;
+#ifndef NAT_REGS_AUX
+#define NAT_REGS_AUX 40
+#endif
+constexpr int REGS_EPI = NAT_REGS_EPI, REGS_UPD = NAT_REGS_UPD, REGS_AUX = NAT_REGS_AUX;
 static_assert(WARP_MMA + 1 <= NUM_THREADS / 32 && EPI_WARPS == 4 && UPD_WARPS % 4 == 0 && BLOCK_M % UPD_WARPS == 0 &&
               2 * (BLOCK_M / UPD_WARPS) <= 32, "warpgroup layout");
 static_assert(REGS_EPI + (UPD_WARPS / 4) * REGS_UPD + REGS_AUX <= (NUM_THREADS / 128) * LAUNCH_REGS, "setmaxnreg only moves registers inside the CTA: the total must not exceed the launch allocation");
