@@ -196,6 +196,15 @@ int nat_ndjson_emit_frames(const void* sem_codes_host, const void* ac_codes_host
 void nat_free_host(void* p);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Time-base alignment before quantisation
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* out[row, i] = linear interpolation of x[row, :] at T_out points: F.interpolate(x, size=T_out, mode='linear',
+ * align_corners=False) on [B, C, T] features (nat.py:3225-3236), rows = B * C, with the floating-point steps of the
+ * reference's CPU call (bit-identical to torch 2.11 CPU). */
+int nat_interp_linear_f32(const float* x_dev, int64_t rows, int64_t t_in, int64_t t_out, float* out_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Token statistics over the index streams
  * ------------------------------------------------------------------------------------------------------------- */
 

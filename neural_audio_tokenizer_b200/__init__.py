@@ -12,7 +12,8 @@ from .ndjson import create_ndjson_stream, emit_frame_lines
 from .quantizers import ResidualVectorQuantizer, VectorQuantizer
 from .sharding import all_gather_codes, shard_range
 from . import token_stats
+from .align import align_time_bases, interpolate_linear
 
 __all__ = ["ResidualVectorQuantizer", "VectorQuantizer", "MelSpectrogram", "spectral_stats", "install",
-           "patch_reference_module", "all_gather_codes", "shard_range", "create_ndjson_stream", "emit_frame_lines", "token_stats"]
+           "patch_reference_module", "all_gather_codes", "shard_range", "create_ndjson_stream", "emit_frame_lines", "token_stats", "align_time_bases", "interpolate_linear"]
 __version__ = "0.1.0"

@@ -47,6 +47,7 @@ _SIGNATURES = [
     ("nat_spectral_num_frames", c_int64, [c_int64, c_int, c_int]),
     ("nat_debug_rvq_scores", c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_size_t, c_void_p]),
+    ("nat_interp_linear_f32", c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     ("nat_token_histogram", c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     ("nat_token_joint_histogram", c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     ("nat_ndjson_emit_frames", c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_int, c_int, c_int,

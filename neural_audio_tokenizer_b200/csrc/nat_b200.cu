@@ -25,6 +25,7 @@
 #include "rvq_rows.cuh"
 #include "rvq_stack_sm100.cuh"
 #include "token_stats.cuh"
+#include "interp.cuh"
 
 namespace {
 
@@ -723,6 +724,26 @@ int nat_rvq_decode_f32(const nat_rvq_codebooks* cb, const void* codes_dev, int c
     const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, cb->sm_count * 16));
     NAT_LAUNCH(5, static_cast<cudaStream_t>(stream), rows::decode_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         cb->cbf, static_cast<long long>(cb->K) * cb->dp, cb->dp, cb->D, used, codes_dev, code_dtype, N, T, layout, out_dev));
+    NAT_CUDA(cudaGetLastError());
+    return NAT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- time alignment
+int nat_interp_linear_f32(const float* x_dev, int64_t rows, int64_t t_in, int64_t t_out, float* out_dev, void* stream) {
+    using namespace nat;
+    if (rows < 0 || t_in < 1 || t_out < 0 || t_in > 0x7FFFFFFF || t_out > 0x7FFFFFFF)
+        return fail(NAT_ERR_INVALID_ARGUMENT, "bad extents for linear interpolation");
+    if (rows == 0 || t_out == 0) return NAT_OK;
+    if (x_dev == nullptr || out_dev == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null device pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int dev = 0, sms = 148;
+    NAT_CUDA(cudaGetDevice(&dev));
+    NAT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const float scale = static_cast<float>(t_in) / static_cast<float>(t_out);   // area_pixel_compute_scale<float>
+    const long long total = rows * t_out;
+    const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>((total + 255) / 256, sms * 16)));
+    NAT_LAUNCH(5, st, interp::interp_linear_kernel<<<grid, 256, 0, st>>>(x_dev, rows, static_cast<int>(t_in),
+                                                                        static_cast<int>(t_out), scale, out_dev));
     NAT_CUDA(cudaGetLastError());
     return NAT_OK;
 }

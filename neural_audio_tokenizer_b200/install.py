@@ -81,3 +81,5 @@ def patch_reference_module(nat_module) -> None:
     nat_module.T = shim
     from . import ndjson
     ndjson.install(nat_module)                      # StreamingProtocol.create_ndjson_stream -> native emitter
+    from . import align
+    align.install(nat_module)                       # the time-base alignment F.interpolate (nat.py:3230-3236)

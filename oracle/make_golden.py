@@ -253,6 +253,22 @@ def token_stats_cases(nat) -> None:
     print("token_stats:", {k: (round(v["semantic_entropy"], 4), round(v["mutual_information"], 4)) for k, v in cases.items()})
 
 
+INTERP_CASES = [(44, 3), (3, 44), (100, 97), (2250, 2249), (1000, 333), (7, 7), (513, 1024), (1, 5), (4410, 4307)]
+
+
+def interp_cases(nat) -> None:
+    """The reference's time-base alignment call (nat.py:3230: F.interpolate(..., mode='linear', align_corners=False))
+    on seeded [2, 2, T] features, through the reference module's own `F`."""
+    out = {}
+    for n, (t_in, t_out) in enumerate(INTERP_CASES):
+        x = torch.randn(2, 2, t_in, generator=torch.Generator().manual_seed(100 + n))
+        y = nat.F.interpolate(x, size=t_out, mode="linear", align_corners=False)
+        out[f"x_{t_in}_{t_out}"] = x.numpy()
+        out[f"y_{t_in}_{t_out}"] = y.numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "interp_cases.npz"), **out)
+    print("interp_cases:", len(INTERP_CASES))
+
+
 def sampling_cases(nat) -> None:
     rvq_sampling_case(nat, "rvq_sampling_small", seed=7, D=64, K=128, L=4, T=300, noise_seed=99)
     rvq_sampling_case(nat, "rvq_sampling_mixed", seed=8, D=48, K=100, L=4, T=120, noise_seed=5, argmin_layers=(1, 3))
@@ -271,6 +287,9 @@ def main() -> None:
         return
     if "stats" in sys.argv[1:]:
         token_stats_cases(nat)
+        return
+    if "interp" in sys.argv[1:]:
+        interp_cases(nat)
         return
     rvq_case(nat, "rvq_small", seed=7, D=64, K=128, L=4, B=1, T=50, store_codebooks=True)
     rvq_case(nat, "rvq_ragged", seed=11, D=80, K=300, L=3, B=2, T=37, store_codebooks=True)
@@ -296,6 +315,7 @@ def main() -> None:
     ndjson_cases(nat)
     sampling_cases(nat)
     token_stats_cases(nat)
+    interp_cases(nat)
 
 
 if __name__ == "__main__":
