@@ -180,6 +180,16 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly one JSON line: whatever libraries print there meanwhile (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(obj), flush=True)
+        os.dup2(2, 1)
 
     import torch.distributed as dist
     from neural_audio_tokenizer_b200 import _lib
@@ -248,9 +258,9 @@ def main():
 
     if args.kernel_only:
         if rank == 0:
-            print(json.dumps({"metric": "rvq_frames_per_sec_8_layers", "value": value, "unit": "frames/s",
-                              "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-                              "gpu_launches": int(launches), "kernel_only": True}))
+            emit({"metric": "rvq_frames_per_sec_8_layers", "value": value, "unit": "frames/s",
+                  "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+                  "gpu_launches": int(launches), "kernel_only": True})
         if world > 1:
             dist.destroy_process_group()
         return
@@ -347,7 +357,7 @@ def main():
                                 "sample": f"{min(CPU_BASELINE_FRAMES, n_local)} frames of the same workload (all of it), one "
                                           f"pass, {sec:.1f} s (oracle/rvq_oracle.py, torch CPU, {cores} threads of "
                                           f"{os.cpu_count()} logical CPUs)"}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
