@@ -48,7 +48,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if proc.returncode != 0:
         raise RuntimeError(f"nvcc failed with exit code {proc.returncode}")
     with open(os.path.join(PKG_DIR, "libnat_b200.ptxas.log"), "w") as f:
-        f.write(proc.stdout + proc.stderr)
+        # registers / spills / shared memory per kernel; compile times vary from run to run and are left out
+        f.write("".join(l for l in (proc.stdout + proc.stderr).splitlines(True) if "Compile time" not in l))
     return LIB_PATH
 
 
