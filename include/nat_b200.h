@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define NAT_B200_ABI_VERSION 1
+#define NAT_B200_ABI_VERSION 2
 
 enum nat_status {
     NAT_OK = 0,
@@ -147,10 +147,45 @@ unsigned long long nat_launch_count(void);
 int nat_rvq_decode_f32(const nat_rvq_codebooks* cb, const void* codes_dev, int code_dtype, int n_code_layers,
                        int64_t B, int64_t T, int layout, float* out_dev, void* stream);
 
-/* Host-buffer form of nat_rvq_encode_f32 (the end-to-end call: H2D of features and D2H of indices inside).
- * x_host / codes_out_host are host pointers (pinned memory overlaps copies with compute; pageable works). */
+/* Host-buffer form of nat_rvq_encode_f32 for one stack (H2D of features and D2H of indices inside).
+ * x_host / codes_out_host are host pointers (pinned memory overlaps copies with compute; pageable works). Uses a
+ * context private to the handle, one call at a time (serialised); nat_tokenize_host_f32 below is the general form. */
 int nat_rvq_encode_host_f32(const nat_rvq_codebooks* cb, const float* x_host, int layout, int64_t B, int64_t T,
                             void* codes_out_host, int code_dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * The stacks of one tokenizer in one call
+ * Replaces the pair of calls `self.semantic_quantizer(...)`, `self.acoustic_quantizer(...)` at nat.py:3239-3240
+ * (codes only: the form `encode` / the tokenise path needs, nat.py:1422-1426).
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* Encode B*T frames through n_stacks stacks (n_stacks <= 2: S0-S3 and A0-A3).
+ *   x_dev[i]         features of stack i in `layout`; stacks given the SAME pointer share one layer-0 preparation
+ *   codes_out_dev    [sum_i L_i, B*T] integers of `code_dtype`: stack 0's streams, then stack 1's
+ * Stacks with equal codebook_size and input_dim (<= 1024) run in ONE persistent launch per chunk of frames; other
+ * shapes, inputs of a few tiles and NAT_RVQ_EXACT_SCAN run stack after stack as nat_rvq_encode_f32 would. */
+size_t nat_rvq_stacks_workspace_bytes(const nat_rvq_codebooks* const* stacks, int n_stacks, int64_t n_frames);
+int nat_rvq_encode_stacks_f32(const nat_rvq_codebooks* const* stacks, int n_stacks, const float* const* x_dev,
+                              int layout, int64_t B, int64_t T, void* codes_out_dev, int code_dtype,
+                              void* workspace_dev, size_t workspace_bytes, int flags, void* stream);
+/* Same call, timed per kernel class like nat_rvq_encode_profile_f32 (bench.py's roofline leg). */
+int nat_rvq_encode_stacks_profile_f32(const nat_rvq_codebooks* const* stacks, int n_stacks, const float* const* x_dev,
+                                      int layout, int64_t B, int64_t T, void* codes_out_dev, int code_dtype,
+                                      void* workspace_dev, size_t workspace_bytes, int flags, void* stream,
+                                      float* prof_ms_host);
+
+/* Host-buffer form (the end-to-end call): H2D of the features and D2H of the index streams inside.
+ * A nat_host_ctx owns the device staging arena, the copy stream and the events of such calls; it serves one call at
+ * a time, so concurrent callers (one per stream / thread) each create their own. Nothing is kept on the codebook
+ * handles, which stay shareable across streams.
+ *   x_host           features, host memory (pinned memory overlaps the copies with compute; pageable works); every
+ *                    chunk is uploaded once and all stacks run on it
+ *   codes_out_host   [sum_i L_i, B*T] of `code_dtype`; has landed when the call returns */
+typedef struct nat_host_ctx nat_host_ctx;
+int nat_host_ctx_create(nat_host_ctx** out);
+int nat_host_ctx_destroy(nat_host_ctx* ctx);
+int nat_tokenize_host_f32(nat_host_ctx* ctx, const nat_rvq_codebooks* const* stacks, int n_stacks, const float* x_host,
+                          int layout, int64_t B, int64_t T, void* codes_out_host, int code_dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Front-end

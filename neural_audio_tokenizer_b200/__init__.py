@@ -11,9 +11,10 @@ from .install import install, patch_reference_module
 from .ndjson import create_ndjson_stream, emit_frame_lines
 from .quantizers import ResidualVectorQuantizer, VectorQuantizer
 from .sharding import all_gather_codes, shard_range
+from .stacks import HostContext, encode_stacks, encode_stacks_host
 from . import token_stats
 from .align import align_time_bases, interpolate_linear
 
 __all__ = ["ResidualVectorQuantizer", "VectorQuantizer", "MelSpectrogram", "spectral_stats", "install",
-           "patch_reference_module", "all_gather_codes", "shard_range", "create_ndjson_stream", "emit_frame_lines", "token_stats", "align_time_bases", "interpolate_linear"]
+           "patch_reference_module", "all_gather_codes", "shard_range", "create_ndjson_stream", "emit_frame_lines", "token_stats", "align_time_bases", "interpolate_linear", "encode_stacks", "encode_stacks_host", "HostContext"]
 __version__ = "0.1.0"

@@ -40,6 +40,16 @@ _SIGNATURES = [
     ("nat_launch_count", ctypes.c_ulonglong, []),
     ("nat_rvq_decode_f32", c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     ("nat_rvq_encode_host_f32", c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_int, c_void_p]),
+    ("nat_rvq_stacks_workspace_bytes", c_size_t, [POINTER(c_void_p), c_int, c_int64]),
+    ("nat_rvq_encode_stacks_f32", c_int, [POINTER(c_void_p), c_int, POINTER(c_void_p), c_int, c_int64, c_int64, c_void_p,
+                                          c_int, c_void_p, c_size_t, c_int, c_void_p]),
+    ("nat_rvq_encode_stacks_profile_f32", c_int, [POINTER(c_void_p), c_int, POINTER(c_void_p), c_int, c_int64, c_int64,
+                                                  c_void_p, c_int, c_void_p, c_size_t, c_int, c_void_p,
+                                                  POINTER(c_float)]),
+    ("nat_host_ctx_create", c_int, [POINTER(c_void_p)]),
+    ("nat_host_ctx_destroy", c_int, [c_void_p]),
+    ("nat_tokenize_host_f32", c_int, [c_void_p, POINTER(c_void_p), c_int, c_void_p, c_int, c_int64, c_int64, c_void_p,
+                                      c_int, c_void_p]),
     ("nat_mel_power_f32", c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                   c_void_p, c_void_p]),
     ("nat_spectral_stats_f32", c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -11,7 +11,7 @@ import sys
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(PKG_DIR, "libnat_b200.so")
+LIB_PATH = os.environ.get("NAT_B200_LIB_OUT") or os.path.join(PKG_DIR, "libnat_b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -20,6 +20,11 @@ NVCC_FLAGS = [
     "-Xptxas", "-v",
     "--expt-relaxed-constexpr",
 ]
+
+
+def extra_flags():
+    """A/B builds: NAT_B200_NVCC_FLAGS="-DNAT_REGS_UPD=88 ..." (with NAT_B200_LIB_OUT naming the output)."""
+    return os.environ.get("NAT_B200_NVCC_FLAGS", "").split()
 
 
 def sources():
@@ -41,12 +46,16 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libnat_b200.so (there is no CPU fallback)")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB_PATH, *sources()]
+    tmp = LIB_PATH + ".tmp"                      # built aside and renamed: a snapshot never sees a half-written library
+    cmd = [nvcc, *NVCC_FLAGS, *extra_flags(), "-o", tmp, *sources()]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)
     if proc.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError(f"nvcc failed with exit code {proc.returncode}")
+    os.replace(tmp, LIB_PATH)
     with open(os.path.join(PKG_DIR, "libnat_b200.ptxas.log"), "w") as f:
         # registers / spills / shared memory per kernel; compile times vary from run to run and are left out
         f.write("".join(l for l in (proc.stdout + proc.stderr).splitlines(True) if "Compile time" not in l))

@@ -171,8 +171,10 @@ static cudaError_t stack_kernel_attrs() {
 }
 
 // One persistent launch of the fused stack kernel: plain grid (pair == 1) or clusters of two CTAs (pair == 2).
+struct StackMaps { CUtensorMap a0, a1, aw0, aw1, b0, b1; };
+
 template <int NV>
-static cudaError_t launch_stack(int pair, int grid, cudaStream_t st, const CUtensorMap& map_a, const CUtensorMap& map_b,
+static cudaError_t launch_stack(int pair, int grid, cudaStream_t st, const StackMaps& m,
                                 const nat::stack::StackArgs& sa) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
@@ -190,11 +192,22 @@ static cudaError_t launch_stack(int pair, int grid, cudaStream_t st, const CUten
     // the instrumented instantiation runs only while counters or timing experiments are switched on
     const bool dbg = sa.dbg != nullptr || sa.dbg_mode != 0;
     if (pair == 2)
-        return dbg ? cudaLaunchKernelEx(&cfg, nat::stack::rvq_stack_kernel<NV, 2, true>, map_a, map_b, sa)
-                   : cudaLaunchKernelEx(&cfg, nat::stack::rvq_stack_kernel<NV, 2, false>, map_a, map_b, sa);
-    return dbg ? cudaLaunchKernelEx(&cfg, nat::stack::rvq_stack_kernel<NV, 1, true>, map_a, map_b, sa)
-               : cudaLaunchKernelEx(&cfg, nat::stack::rvq_stack_kernel<NV, 1, false>, map_a, map_b, sa);
+        return dbg ? cudaLaunchKernelEx(&cfg, nat::stack::rvq_stack_kernel<NV, 2, true>, m.a0, m.a1, m.aw0, m.aw1, m.b0, m.b1, sa)
+                   : cudaLaunchKernelEx(&cfg, nat::stack::rvq_stack_kernel<NV, 2, false>, m.a0, m.a1, m.aw0, m.aw1, m.b0, m.b1, sa);
+    return dbg ? cudaLaunchKernelEx(&cfg, nat::stack::rvq_stack_kernel<NV, 1, true>, m.a0, m.a1, m.aw0, m.aw1, m.b0, m.b1, sa)
+               : cudaLaunchKernelEx(&cfg, nat::stack::rvq_stack_kernel<NV, 1, false>, m.a0, m.a1, m.aw0, m.aw1, m.b0, m.b1, sa);
 }
+
+// Caller-owned state of the host-buffer entry points: a two-slot device staging arena (grown on demand), the copy
+// stream and the events that order H2D / compute / D2H. One context serves one call at a time; concurrent calls on
+// different streams use different contexts (nothing of this lives on the shared codebook handles).
+struct nat_host_ctx {
+    int device = -1;
+    void* arena = nullptr;
+    size_t arena_bytes = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
 
 struct nat_rvq_codebooks {
     int L, K, D, dp, kp, device, sm_count;
@@ -209,11 +222,10 @@ struct nat_rvq_codebooks {
     bool pair_ok;                     // the device can co-schedule the two-CTA clusters of the fused kernel
     unsigned long long* stack_dbg;    // [sm_count][DBG_SLOTS] cycle counters of the last fused launch (debug hook)
     bool stack_dbg_on;
-    // staging arena of the host-buffer entry point (grown on first use)
-    void* host_arena_dev;
-    size_t host_arena_bytes;
-    cudaStream_t copy_stream;
-    cudaEvent_t ev[4];
+    // nat_rvq_encode_host_f32 (one stack, no caller context): a private host context, created on first use and
+    // serialised by a mutex -- concurrent host-buffer calls should bring their own nat_host_ctx
+    struct nat_host_ctx* host_ctx;
+    std::mutex* host_mutex;
     // internal streams of the two-lane encode (created on first use)
     cudaStream_t side[2];
     cudaEvent_t side_ev[3];
@@ -272,6 +284,7 @@ int nat_rvq_codebooks_create(const float* const* codebooks_dev, int L, int K, in
     cb->L = L; cb->K = K; cb->D = D;
     cb->dp = static_cast<int>(round_up(D, 64));
     cb->kp = static_cast<int>(round_up(K, 256));
+    cb->host_mutex = new std::mutex();
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc = NAT_OK;
     auto guard = [&](cudaError_t e, const char* what) {
@@ -295,10 +308,14 @@ int nat_rvq_codebooks_create(const float* const* codebooks_dev, int L, int K, in
                                    nat::gemm::SMEM_BYTES), "cudaFuncSetAttribute");
         guard(cudaFuncSetAttribute(nat::gemm::rvq_gemm_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    nat::gemm::SMEM_BYTES), "cudaFuncSetAttribute");
+#ifdef NAT_ONLY_NV
+        guard(stack_kernel_attrs<NAT_ONLY_NV>(), "cudaFuncSetAttribute");
+#else
         guard(stack_kernel_attrs<2>(), "cudaFuncSetAttribute");
         guard(stack_kernel_attrs<4>(), "cudaFuncSetAttribute");
         guard(stack_kernel_attrs<6>(), "cudaFuncSetAttribute");
         guard(stack_kernel_attrs<8>(), "cudaFuncSetAttribute");
+#endif
         {   // CTA pairs need two co-resident CTAs of 768 threads / 224 KB in one cluster (a TPC); ask the runtime
             cudaLaunchConfig_t cfg;
             memset(&cfg, 0, sizeof cfg);
@@ -337,9 +354,9 @@ int nat_rvq_codebooks_update(nat_rvq_codebooks* cb, const float* const* codebook
 int nat_rvq_codebooks_destroy(nat_rvq_codebooks* cb) {
     if (cb == nullptr) return NAT_OK;
     cudaFree(cb->cbf); cudaFree(cb->cbh); cudaFree(cb->cn32); cudaFree(cb->cn64); cudaFree(cb->lc);
-    cudaFree(cb->scratch); cudaFree(cb->host_arena_dev); cudaFree(cb->stack_dbg);
-    if (cb->copy_stream) cudaStreamDestroy(cb->copy_stream);
-    for (auto& e : cb->ev) if (e) cudaEventDestroy(e);
+    cudaFree(cb->scratch); cudaFree(cb->stack_dbg);
+    if (cb->host_ctx) nat_host_ctx_destroy(cb->host_ctx);
+    delete cb->host_mutex;
     for (auto& s2 : cb->side) if (s2) cudaStreamDestroy(s2);
     for (auto& e : cb->side_ev) if (e) cudaEventDestroy(e);
     delete cb;
@@ -371,23 +388,26 @@ size_t nat_rvq_workspace_bytes(const nat_rvq_codebooks* cb, int64_t n_frames) {
 }
 
 // ------------------------------------------------------------------------------------------------- encode
+// Layer-0 preparation of frames [n0, n0 + n): fp32 rows, fp16 operand rows, {alpha, bias, window} and max |x| per
+// frame. `rowinfo_b` / `lc_b`: a second stack quantising the same frames gets its own window from the same sums.
 static int launch_layer0_prep(const nat_rvq_codebooks* cb, const Workspace& ws, const float* x, int layout,
-                              long long T, long long n0, int n, cudaStream_t st) {
+                              long long T, long long n0, int n, cudaStream_t st, float4* rowinfo_b = nullptr,
+                              const nat::rows::LayerConst* lc_b = nullptr) {
     using namespace nat;
     const int warps_grid = std::min((n + 7) / 8, cb->sm_count * 16);
     if (layout == NAT_LAYOUT_ROWS) {
         NAT_LAUNCH(0, st, rows::prep_rows_kernel<<<warps_grid, 256, 0, st>>>(x + n0 * cb->D, cb->D, n, cb->D, cb->dp, ws.r, ws.a,
-                                                           ws.rowinfo, ws.rowamax, cb->lc, false));
+                                                           ws.rowinfo, ws.rowamax, cb->lc, false, rowinfo_b, lc_b));
     } else {
         const size_t smem = static_cast<size_t>(rows::kPrepFrames) * (cb->dp + 1) * sizeof(float);
         if (smem <= 200 * 1024) {
             NAT_LAUNCH(0, st, rows::prep_bct_fused_kernel<<<(n + rows::kPrepFrames - 1) / rows::kPrepFrames, rows::kPrepThreads, smem, st>>>(
-                x, T, cb->D, n0, n, cb->dp, ws.r, ws.a, ws.rowinfo, ws.rowamax, cb->lc));
+                x, T, cb->D, n0, n, cb->dp, ws.r, ws.a, ws.rowinfo, ws.rowamax, cb->lc, rowinfo_b, lc_b));
         } else {
             dim3 grid((n + 31) / 32, cb->dp / 32);
             NAT_LAUNCH(0, st, rows::bct_to_rows_kernel<<<grid, 256, 0, st>>>(x, T, cb->D, n0, n, cb->dp, ws.r));
             NAT_LAUNCH(0, st, rows::prep_rows_kernel<<<warps_grid, 256, 0, st>>>(nullptr, 0, n, cb->D, cb->dp, ws.r, ws.a,
-                                                                              ws.rowinfo, ws.rowamax, cb->lc, true));
+                                                                              ws.rowinfo, ws.rowamax, cb->lc, true, rowinfo_b, lc_b));
         }
     }
     NAT_CUDA(cudaGetLastError());
@@ -410,6 +430,88 @@ static int fused_group(int pair) {
     const char* e = getenv("NAT_RVQ_GROUP");
     const int v = e ? atoi(e) : 0;
     return v >= 1 ? v : (pair == 2 ? 3 : 2);      // measured on B200: 270k x 768, K = 1024 (profiles/)
+}
+
+// One launch of the fused stack kernel over up to two stacks (same K / D) on the same frame range.
+struct StackLaunch {
+    const nat_rvq_codebooks* cb[nat::stack::MAX_STACKS] = {nullptr, nullptr};
+    int n_stacks = 1;
+    const float* r0[2] = {nullptr, nullptr};
+    const float4* rowinfo0[2] = {nullptr, nullptr};
+    const float* rowamax0[2] = {nullptr, nullptr};
+    float* r_work[2] = {nullptr, nullptr}; __half* a_work[2] = {nullptr, nullptr};
+    float4* rowinfo_work[2] = {nullptr, nullptr}; float* rowamax_work[2] = {nullptr, nullptr};
+    void* codes[2] = {nullptr, nullptr}; long long codes_ld[2] = {0, 0}, code_off[2] = {0, 0};
+    double* row_loss[2] = {nullptr, nullptr}; long long loss_ld = 0;
+    unsigned long long* stats[2] = {nullptr, nullptr};
+    StackMaps maps;              // a0 / a1 / aw0 / aw1 filled by the caller; b0 / b1 come from the handles
+    int n_rows = 0, code_dtype = NAT_CODES_I16;
+};
+
+static int launch_fused_stacks(StackLaunch& sl, cudaStream_t st) {
+    using namespace nat;
+    const nat_rvq_codebooks* cb = sl.cb[0];
+    const int n_tiles = (sl.n_rows + stack::BLOCK_M - 1) / stack::BLOCK_M;
+    stack::StackArgs sa;
+    memset(&sa, 0, sizeof sa);
+    sa.n_stacks = sl.n_stacks;
+    for (int i = 0; i < sl.n_stacks; ++i) {
+        const nat_rvq_codebooks* c = sl.cb[i];
+        stack::StackRef& r = sa.s[i];
+        r.cbf = c->cbf; r.cn64 = c->cn64; r.cn32 = c->cn32; r.lc = c->lc;
+        r.r0 = sl.r0[i]; r.rowinfo0 = sl.rowinfo0[i]; r.rowamax0 = sl.rowamax0[i];
+        r.r_work = sl.r_work[i]; r.a_work = sl.a_work[i]; r.rowinfo_work = sl.rowinfo_work[i]; r.rowamax_work = sl.rowamax_work[i];
+        r.codes = sl.codes[i]; r.codes_ld = sl.codes_ld[i]; r.code_off = sl.code_off[i];
+        r.row_loss = sl.row_loss[i]; r.loss_ld = sl.loss_ld;
+        r.stats = sl.stats[i];
+        r.L = c->L;
+        // Residual write-back policy of the hot update form: the residual entering the last layer is never needed in
+        // memory (only its fp16 operand is); which of the other layers write it back is a measured choice (a layer
+        // whose bit is clear leaves later layers to replay its update from the emitted code: one extra L2 gather).
+        r.store_mask = 0x55555555 & ((1 << std::max(0, c->L - 2)) - 1);
+        { const char* e = getenv("NAT_RVQ_STORE_MASK"); if (e) r.store_mask &= atoi(e); }
+        { const char* e = getenv("NAT_RVQ_STORE_MASK_SET"); if (e) r.store_mask = atoi(e); }      // A/B measurements
+    }
+    sa.n_rows = sl.n_rows; sa.n_tiles = n_tiles; sa.K = cb->K; sa.kp = cb->kp; sa.dp = cb->dp;
+    sa.code_dtype = sl.code_dtype;
+    bool dbg_on = false;
+    for (int i = 0; i < sl.n_stacks; ++i) dbg_on = dbg_on || sl.cb[i]->stack_dbg_on;
+    sa.dbg = dbg_on ? cb->stack_dbg : nullptr;
+    { const char* e = getenv("NAT_RVQ_DBG_MODE"); sa.dbg_mode = e ? atoi(e) : 0; }
+    // CTA pairs (one tcgen05.mma.cta_group::2 per two SMs) once there is more than one tile; NAT_RVQ_PAIR=1 keeps
+    // the single-CTA form for A/B measurements.
+    const int pair = (n_tiles >= 2 && cb->sm_count >= 2 && cb->pair_ok && fused_pair()) ? 2 : 1;
+    // one stack: as many CTAs as tiles, up to one per SM. Two stacks: the SMs are split between them (whole CTA
+    // pairs), each half at most as many CTAs as there are tiles.
+    int grid, split;
+    if (sl.n_stacks == 1) {
+        grid = pair == 2 ? std::min((n_tiles + 1) & ~1, cb->sm_count & ~1) : std::min(n_tiles, cb->sm_count);
+        split = grid;
+    } else {
+        const int half = pair == 2 ? std::min((n_tiles + 1) & ~1, (cb->sm_count / 2) & ~1) : std::min(n_tiles, cb->sm_count / 2);
+        split = half;
+        grid = 2 * half;
+    }
+    sa.split = split;
+    sl.maps.b0 = pair == 2 ? sl.cb[0]->map_b_half : sl.cb[0]->map_b;
+    const nat_rvq_codebooks* cb1 = sl.cb[sl.n_stacks > 1 ? 1 : 0];
+    sl.maps.b1 = pair == 2 ? cb1->map_b_half : cb1->map_b;
+    sa.group = fused_group(pair);
+    const int nv = (cb->dp / 4 + 31) / 32;
+    cudaError_t le = cudaSuccess;
+    NAT_LAUNCH(1, st, {
+#ifdef NAT_ONLY_NV                                   /* A/B builds: one instantiation, a quarter of the compile time */
+        le = launch_stack<NAT_ONLY_NV>(pair, grid, st, sl.maps, sa);
+#else
+        if (nv <= 2) le = launch_stack<2>(pair, grid, st, sl.maps, sa);
+        else if (nv <= 4) le = launch_stack<4>(pair, grid, st, sl.maps, sa);
+        else if (nv <= 6) le = launch_stack<6>(pair, grid, st, sl.maps, sa);
+        else le = launch_stack<8>(pair, grid, st, sl.maps, sa);
+#endif
+    });
+    NAT_CUDA(le);
+    NAT_CUDA(cudaGetLastError());
+    return NAT_OK;
 }
 
 // Everything one chunk of frames [n0, n0 + n) needs, in order, on one stream.
@@ -435,38 +537,17 @@ static int encode_chunk(const EncodeCall& c, const Workspace& ws, const CUtensor
     const bool fused = !c.exact && c.temperatures == nullptr && fused_enabled() && cb->dp <= 1024 && c.scores == nullptr;
     if (!fused) NAT_CUDA(cudaMemsetAsync(ws.scan_count, 0, sizeof(int) * cb->L, st));   // only the per-layer kernels list scans
     if (fused) {
-        // one persistent launch for all L layers (rvq_stack_sm100.cuh)
-        stack::StackArgs sa;
-        sa.cbf = cb->cbf; sa.cn64 = cb->cn64; sa.cn32 = cb->cn32; sa.lc = cb->lc;
-        sa.r = ws.r; sa.a = ws.a; sa.rowinfo = ws.rowinfo; sa.rowamax = ws.rowamax;
-        sa.codes = c.codes; sa.codes_ld = c.N; sa.code_off = n0;
-        sa.row_loss = c.want_loss ? ws.row_loss : nullptr; sa.loss_ld = ws.rows;
-        sa.stats = c.stats;
-        sa.n_rows = n; sa.n_tiles = n_tiles; sa.L = cb->L; sa.K = cb->K; sa.kp = cb->kp; sa.dp = cb->dp;
-        sa.code_dtype = c.code_dtype;
-        sa.dbg = cb->stack_dbg_on ? cb->stack_dbg : nullptr;
-        { const char* e = getenv("NAT_RVQ_DBG_MODE"); sa.dbg_mode = e ? atoi(e) : 0; }
-        // Residual write-back policy of the hot update form: the residual entering the last layer is never needed in
-        // memory (only its fp16 operand is), and writing back after every other layer only (later layers replay the
-        // skipped update from the emitted code, one extra L2 gather) measured faster than every layer or none.
-        sa.store_mask = 0x55555555 & ((1 << std::max(0, cb->L - 2)) - 1);
-        { const char* e = getenv("NAT_RVQ_STORE_MASK"); if (e) sa.store_mask &= atoi(e); }
-        // CTA pairs (one tcgen05.mma.cta_group::2 per two SMs) once there is more than one tile; NAT_RVQ_PAIR=1 keeps
-        // the single-CTA form for A/B measurements.
-        const int pair = (n_tiles >= 2 && cb->sm_count >= 2 && cb->pair_ok && fused_pair()) ? 2 : 1;
-        const int grid = pair == 2 ? std::min((n_tiles + 1) & ~1, cb->sm_count & ~1) : std::min(n_tiles, cb->sm_count);
-        const CUtensorMap& map_b = pair == 2 ? cb->map_b_half : cb->map_b;
-        sa.group = fused_group(pair);
-        const int nv = (cb->dp / 4 + 31) / 32;
-        cudaError_t le = cudaSuccess;
-        NAT_LAUNCH(1, st, {
-            if (nv <= 2) le = launch_stack<2>(pair, grid, st, map_a, map_b, sa);
-            else if (nv <= 4) le = launch_stack<4>(pair, grid, st, map_a, map_b, sa);
-            else if (nv <= 6) le = launch_stack<6>(pair, grid, st, map_a, map_b, sa);
-            else le = launch_stack<8>(pair, grid, st, map_a, map_b, sa);
-        });
-        NAT_CUDA(le);
-        NAT_CUDA(cudaGetLastError());
+        // one persistent launch for all L layers (rvq_stack_sm100.cuh); one stack: the update warps write in place
+        StackLaunch sl;
+        sl.cb[0] = cb; sl.n_stacks = 1;
+        sl.r0[0] = ws.r; sl.rowinfo0[0] = ws.rowinfo; sl.rowamax0[0] = ws.rowamax;
+        sl.r_work[0] = ws.r; sl.a_work[0] = ws.a; sl.rowinfo_work[0] = ws.rowinfo; sl.rowamax_work[0] = ws.rowamax;
+        sl.codes[0] = c.codes; sl.codes_ld[0] = c.N; sl.code_off[0] = n0;
+        sl.row_loss[0] = c.want_loss ? ws.row_loss : nullptr; sl.loss_ld = ws.rows;
+        sl.stats[0] = c.stats;
+        sl.maps.a0 = map_a; sl.maps.a1 = map_a; sl.maps.aw0 = map_a; sl.maps.aw1 = map_a;
+        sl.n_rows = n; sl.code_dtype = c.code_dtype;
+        if (int rc = launch_fused_stacks(sl, st)) return rc;
         if (c.want_loss)
             for (int l = 0; l < cb->L; ++l)
                 NAT_LAUNCH(4, st, rows::reduce_loss_kernel<<<1, 1024, 0, st>>>(ws.row_loss + static_cast<long long>(l) * ws.rows,
@@ -683,18 +764,8 @@ int nat_rvq_sample_f32(const nat_rvq_codebooks* cb, const float* x_dev, int layo
                        temperatures_host, noise_dev, philox_seed, philox_draw);
 }
 
-int nat_rvq_encode_profile_f32(const nat_rvq_codebooks* cb, const float* x_dev, int layout, int64_t B, int64_t T,
-                               void* codes_out_dev, int code_dtype, float* quantized_out_dev, float* loss_out_dev,
-                               float commitment_weight, unsigned long long* stats_dev, void* workspace_dev,
-                               size_t workspace_bytes, int flags, void* stream, float* prof_ms_host) {
-    if (prof_ms_host == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null profile buffer");
-    Profiler prof;
-    g_prof = &prof;
-    const int rc = nat_rvq_encode_f32(cb, x_dev, layout, B, T, codes_out_dev, code_dtype, quantized_out_dev,
-                                      loss_out_dev, commitment_weight, stats_dev, workspace_dev, workspace_bytes, flags,
-                                      stream);
-    g_prof = nullptr;
-    cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+static int finish_profile(Profiler& prof, int rc, cudaStream_t stream, float* prof_ms_host) {
+    cudaError_t e = cudaStreamSynchronize(stream);
     for (int i = 0; i < NAT_PROF_FIELDS; ++i) prof_ms_host[i] = 0.f;
     for (auto& sp : prof.spans) {
         float ms = 0.f;
@@ -707,6 +778,20 @@ int nat_rvq_encode_profile_f32(const nat_rvq_codebooks* cb, const float* x_dev, 
     if (rc != NAT_OK) return rc;
     if (e != cudaSuccess) return fail(NAT_ERR_CUDA, "cudaStreamSynchronize failed: %s", cudaGetErrorString(e));
     return NAT_OK;
+}
+
+int nat_rvq_encode_profile_f32(const nat_rvq_codebooks* cb, const float* x_dev, int layout, int64_t B, int64_t T,
+                               void* codes_out_dev, int code_dtype, float* quantized_out_dev, float* loss_out_dev,
+                               float commitment_weight, unsigned long long* stats_dev, void* workspace_dev,
+                               size_t workspace_bytes, int flags, void* stream, float* prof_ms_host) {
+    if (prof_ms_host == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null profile buffer");
+    Profiler prof;
+    g_prof = &prof;
+    const int rc = nat_rvq_encode_f32(cb, x_dev, layout, B, T, codes_out_dev, code_dtype, quantized_out_dev,
+                                      loss_out_dev, commitment_weight, stats_dev, workspace_dev, workspace_bytes, flags,
+                                      stream);
+    g_prof = nullptr;
+    return finish_profile(prof, rc, static_cast<cudaStream_t>(stream), prof_ms_host);
 }
 
 unsigned long long nat_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
@@ -841,78 +926,280 @@ int nat_debug_rvq_scores(const nat_rvq_codebooks* cb, int layer, const float* ro
     return NAT_OK;
 }
 
-// Host-buffer entry point: frames stream through a two-slot device arena so H2D of chunk i+1 overlaps compute of i.
-int nat_rvq_encode_host_f32(const nat_rvq_codebooks* cb_const, const float* x_host, int layout, int64_t B, int64_t T,
-                            void* codes_out_host, int code_dtype, void* stream) {
-    nat_rvq_codebooks* cb = const_cast<nat_rvq_codebooks*>(cb_const);
-    if (cb == nullptr || x_host == nullptr || codes_out_host == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null argument");
+// ------------------------------------------------------------------------------------------------- several stacks
+// The stacks of one tokenizer (S0-S3, A0-A3) in one call. Stacks that quantise the same frames (equal x pointers)
+// share one layer-0 preparation; all of them share ONE persistent launch of the fused kernel per chunk of frames
+// (stack 1's layers follow stack 0's for every group of tiles). Shapes the fused form does not cover (different K or
+// D, D > 1024, inputs of a few tiles, NAT_RVQ_FUSED=0) run stack after stack through nat_rvq_encode_f32.
+namespace {
+
+bool stacks_fusable(const nat_rvq_codebooks* const* stacks, int n_stacks, long long N) {
+    if (n_stacks != 2 || !fused_enabled()) return false;
+    const nat_rvq_codebooks *a = stacks[0], *b = stacks[1];
+    if (a->D != b->D || a->K != b->K || a->dp > 1024 || a->device != b->device) return false;
+    if (small_path_enabled() && small_input_scores_bytes(a, N) != 0) return false;     // latency path wins there
+    return true;
+}
+
+struct MultiWs {
+    float* r_prep[2]; __half* a_prep[2]; float* rowamax[2]; float4* rowinfo[2];
+    float* r_work[2]; __half* a_work[2]; float4* rowinfo_work[2]; float* rowamax_work[2];
+    long long rows;
+};
+
+// per frame: prepared rows (fp32 + fp16 + max) per distinct input, a layer-0 window per stack, and the rows the
+// update warps write (fp32 + fp16 + window + max) for each of the two stacks
+size_t multi_per_row(int dp, int n_inputs) {
+    return static_cast<size_t>(n_inputs) * (static_cast<size_t>(dp) * 6 + 4) + 2 * 16 +
+           2 * (static_cast<size_t>(dp) * 6 + 16 + 4);
+}
+
+bool carve_multi(void* base, size_t bytes, int dp, int n_inputs, long long want_rows, MultiWs* ws) {
+    const size_t slack = 256 * 20;
+    if (bytes <= slack) return false;
+    long long rows = static_cast<long long>((bytes - slack) / multi_per_row(dp, n_inputs));
+    rows = std::min(rows, round_up(want_rows, 128)) / 128 * 128;
+    if (rows < 128) return false;
+    char* p = static_cast<char*>(base);
+    auto take = [&](size_t n) { char* q = p; p += round_up((long long)n, 256); return q; };
+    for (int i = 0; i < 2; ++i) {
+        const int src = i < n_inputs ? i : 0;
+        if (i < n_inputs) {
+            ws->r_prep[i] = reinterpret_cast<float*>(take(static_cast<size_t>(rows) * dp * 4));
+            ws->a_prep[i] = reinterpret_cast<__half*>(take(static_cast<size_t>(rows) * dp * 2));
+            ws->rowamax[i] = reinterpret_cast<float*>(take(static_cast<size_t>(rows) * 4));
+        } else {
+            ws->r_prep[i] = ws->r_prep[src]; ws->a_prep[i] = ws->a_prep[src]; ws->rowamax[i] = ws->rowamax[src];
+        }
+        ws->rowinfo[i] = reinterpret_cast<float4*>(take(static_cast<size_t>(rows) * 16));
+    }
+    for (int i = 0; i < 2; ++i) {
+        ws->r_work[i] = reinterpret_cast<float*>(take(static_cast<size_t>(rows) * dp * 4));
+        ws->a_work[i] = reinterpret_cast<__half*>(take(static_cast<size_t>(rows) * dp * 2));
+        ws->rowinfo_work[i] = reinterpret_cast<float4*>(take(static_cast<size_t>(rows) * 16));
+        ws->rowamax_work[i] = reinterpret_cast<float*>(take(static_cast<size_t>(rows) * 4));
+    }
+    ws->rows = rows;
+    return static_cast<size_t>(p - static_cast<char*>(base)) <= bytes;
+}
+
+size_t multi_ws_bytes(int dp, int n_inputs, long long n_frames) {
+    const long long rows = std::min<long long>(round_up(n_frames, 128), chunk_cap_rows());
+    return static_cast<size_t>(rows) * multi_per_row(dp, n_inputs) + 256 * 20;
+}
+
+}  // namespace
+
+size_t nat_rvq_stacks_workspace_bytes(const nat_rvq_codebooks* const* stacks, int n_stacks, int64_t n_frames) {
+    size_t need = 0;
+    if (stacks == nullptr) return nat_rvq_workspace_bytes(nullptr, n_frames);
+    for (int i = 0; i < n_stacks; ++i) need = std::max(need, nat_rvq_workspace_bytes(stacks[i], n_frames));
+    if (n_stacks == 2 && stacks[0] != nullptr && stacks[1] != nullptr && n_frames > 0 &&
+        stacks[0]->D == stacks[1]->D && stacks[0]->K == stacks[1]->K && stacks[0]->dp <= 1024)
+        need = std::max(need, multi_ws_bytes(stacks[0]->dp, 2, n_frames));
+    return need;
+}
+
+int nat_rvq_encode_stacks_f32(const nat_rvq_codebooks* const* stacks, int n_stacks, const float* const* x_dev,
+                              int layout, int64_t B, int64_t T, void* codes_out_dev, int code_dtype,
+                              void* workspace_dev, size_t workspace_bytes, int flags, void* stream) {
+    using namespace nat;
+    if (stacks == nullptr || x_dev == nullptr || n_stacks < 1) return fail(NAT_ERR_INVALID_ARGUMENT, "null argument");
+    for (int i = 0; i < n_stacks; ++i)
+        if (stacks[i] == nullptr || x_dev[i] == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "stack %d: null handle or input", i);
+    if (B < 0 || T < 0) return fail(NAT_ERR_INVALID_ARGUMENT, "negative batch or time extent");
+    if (layout != NAT_LAYOUT_BCT && layout != NAT_LAYOUT_ROWS) return fail(NAT_ERR_INVALID_ARGUMENT, "bad layout %d", layout);
+    if (code_dtype < NAT_CODES_I64 || code_dtype > NAT_CODES_I16) return fail(NAT_ERR_INVALID_ARGUMENT, "bad code dtype %d", code_dtype);
+    const long long N = B * T;
+    if (N == 0) return NAT_OK;
+    if (codes_out_dev == nullptr || workspace_dev == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null device pointer");
+    const int cbytes = code_bytes(code_dtype);
+    if (!stacks_fusable(stacks, n_stacks, N) || (flags & NAT_RVQ_EXACT_SCAN)) {
+        long long layer0 = 0;
+        for (int i = 0; i < n_stacks; ++i) {
+            if (int rc = nat_rvq_encode_f32(stacks[i], x_dev[i], layout, B, T, static_cast<char*>(codes_out_dev) + layer0 * N * cbytes,
+                                            code_dtype, nullptr, nullptr, 0.25f, nullptr, workspace_dev, workspace_bytes,
+                                            flags | NAT_RVQ_SINGLE_STREAM, stream)) return rc;
+            layer0 += stacks[i]->L;
+        }
+        return NAT_OK;
+    }
+    const nat_rvq_codebooks *s0 = stacks[0], *s1 = stacks[1];
+    if (code_dtype == NAT_CODES_I16 && s0->K > 32768) return fail(NAT_ERR_INVALID_ARGUMENT, "int16 codes need codebook_size <= 32768");
+    int dev = -1;
+    NAT_CUDA(cudaGetDevice(&dev));
+    if (dev != s0->device) return fail(NAT_ERR_INVALID_ARGUMENT, "codebooks live on device %d, current device is %d", s0->device, dev);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int n_inputs = x_dev[0] == x_dev[1] ? 1 : 2;
+    MultiWs ws;
+    if (!carve_multi(workspace_dev, workspace_bytes, s0->dp, n_inputs, std::min<long long>(N, chunk_cap_rows()), &ws))
+        return fail(NAT_ERR_WORKSPACE, "workspace of %zu bytes cannot hold one 128-frame tile (need %zu)", workspace_bytes,
+                    multi_ws_bytes(s0->dp, n_inputs, 128));
+    StackMaps maps;
+    if (int rc = make_map_f16(&maps.a0, ws.a_prep[0], ws.rows, s0->dp, 128)) return rc;
+    if (n_inputs == 2) { if (int rc = make_map_f16(&maps.a1, ws.a_prep[1], ws.rows, s0->dp, 128)) return rc; }
+    else maps.a1 = maps.a0;
+    if (int rc = make_map_f16(&maps.aw0, ws.a_work[0], ws.rows, s0->dp, 128)) return rc;
+    if (int rc = make_map_f16(&maps.aw1, ws.a_work[1], ws.rows, s0->dp, 128)) return rc;
+    if (s0->dp != s0->D) {          // padded columns of the operand rows are never written by the row kernels
+        for (int i = 0; i < n_inputs; ++i) NAT_CUDA(cudaMemsetAsync(ws.a_prep[i], 0, static_cast<size_t>(ws.rows) * s0->dp * 2, st));
+        for (int i = 0; i < 2; ++i) NAT_CUDA(cudaMemsetAsync(ws.a_work[i], 0, static_cast<size_t>(ws.rows) * s0->dp * 2, st));
+    }
+    for (long long n0 = 0; n0 < N; n0 += ws.rows) {
+        const int n = static_cast<int>(std::min<long long>(ws.rows, N - n0));
+        Workspace w0;
+        memset(&w0, 0, sizeof w0);
+        w0.r = ws.r_prep[0]; w0.a = ws.a_prep[0]; w0.rowinfo = ws.rowinfo[0]; w0.rowamax = ws.rowamax[0]; w0.rows = ws.rows;
+        if (n_inputs == 1) {
+            if (int rc = launch_layer0_prep(s0, w0, x_dev[0], layout, T, n0, n, st, ws.rowinfo[1], s1->lc)) return rc;
+        } else {
+            if (int rc = launch_layer0_prep(s0, w0, x_dev[0], layout, T, n0, n, st)) return rc;
+            Workspace w1 = w0;
+            w1.r = ws.r_prep[1]; w1.a = ws.a_prep[1]; w1.rowinfo = ws.rowinfo[1]; w1.rowamax = ws.rowamax[1];
+            if (int rc = launch_layer0_prep(s1, w1, x_dev[1], layout, T, n0, n, st)) return rc;
+        }
+        StackLaunch sl;
+        sl.n_stacks = 2;
+        for (int i = 0; i < 2; ++i) {
+            sl.cb[i] = stacks[i];
+            sl.r0[i] = ws.r_prep[i]; sl.rowinfo0[i] = ws.rowinfo[i]; sl.rowamax0[i] = ws.rowamax[i];
+            sl.codes[i] = static_cast<char*>(codes_out_dev) + (i == 0 ? 0 : static_cast<long long>(s0->L) * N * cbytes);
+            sl.codes_ld[i] = N; sl.code_off[i] = n0;
+            sl.r_work[i] = ws.r_work[i]; sl.a_work[i] = ws.a_work[i];
+            sl.rowinfo_work[i] = ws.rowinfo_work[i]; sl.rowamax_work[i] = ws.rowamax_work[i];
+        }
+        sl.maps = maps;
+        sl.n_rows = n; sl.code_dtype = code_dtype;
+        if (int rc = launch_fused_stacks(sl, st)) return rc;
+    }
+    return NAT_OK;
+}
+
+int nat_rvq_encode_stacks_profile_f32(const nat_rvq_codebooks* const* stacks, int n_stacks, const float* const* x_dev,
+                                      int layout, int64_t B, int64_t T, void* codes_out_dev, int code_dtype,
+                                      void* workspace_dev, size_t workspace_bytes, int flags, void* stream,
+                                      float* prof_ms_host) {
+    if (prof_ms_host == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null profile buffer");
+    Profiler prof;
+    g_prof = &prof;
+    const int rc = nat_rvq_encode_stacks_f32(stacks, n_stacks, x_dev, layout, B, T, codes_out_dev, code_dtype,
+                                             workspace_dev, workspace_bytes, flags, stream);
+    g_prof = nullptr;
+    return finish_profile(prof, rc, static_cast<cudaStream_t>(stream), prof_ms_host);
+}
+
+// ------------------------------------------------------------------------------------------------- host buffers
+int nat_host_ctx_create(nat_host_ctx** out) {
+    if (out == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    nat_host_ctx* ctx = new nat_host_ctx();
+    cudaError_t e = cudaGetDevice(&ctx->device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    for (auto& ev : ctx->ev)
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        nat_host_ctx_destroy(ctx);
+        return fail(NAT_ERR_CUDA, "host context: %s", cudaGetErrorString(e));
+    }
+    *out = ctx;
+    return NAT_OK;
+}
+
+int nat_host_ctx_destroy(nat_host_ctx* ctx) {
+    if (ctx == nullptr) return NAT_OK;
+    if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+    delete ctx;
+    return NAT_OK;
+}
+
+// Host-buffer entry point: frames stream through the context's two-slot device arena, so the H2D copy of chunk i+1
+// overlaps the kernels of chunk i; every chunk is uploaded ONCE and all stacks run on it; the index streams of all
+// stacks come back as one [sum L, N] host array.
+int nat_tokenize_host_f32(nat_host_ctx* ctx, const nat_rvq_codebooks* const* stacks, int n_stacks, const float* x_host,
+                          int layout, int64_t B, int64_t T, void* codes_out_host, int code_dtype, void* stream) {
+    if (ctx == nullptr || stacks == nullptr || n_stacks < 1 || n_stacks > nat::stack::MAX_STACKS || x_host == nullptr ||
+        codes_out_host == nullptr)
+        return fail(NAT_ERR_INVALID_ARGUMENT, "null argument or unsupported stack count");
     if (code_dtype < NAT_CODES_I64 || code_dtype > NAT_CODES_I16) return fail(NAT_ERR_INVALID_ARGUMENT, "bad code dtype");
+    if (layout != NAT_LAYOUT_BCT && layout != NAT_LAYOUT_ROWS) return fail(NAT_ERR_INVALID_ARGUMENT, "bad layout %d", layout);
+    int L_total = 0;
+    for (int i = 0; i < n_stacks; ++i) {
+        if (stacks[i] == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "stack %d: null handle", i);
+        if (stacks[i]->D != stacks[0]->D) return fail(NAT_ERR_INVALID_ARGUMENT, "stacks fed from one host buffer must share input_dim");
+        L_total += stacks[i]->L;
+    }
     const long long N = B * T;
     if (N <= 0) return NAT_OK;
+    int dev = -1;
+    NAT_CUDA(cudaGetDevice(&dev));
+    if (dev != ctx->device) return fail(NAT_ERR_INVALID_ARGUMENT, "host context belongs to device %d, current device is %d", ctx->device, dev);
+    const int D = stacks[0]->D;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int cbytes = code_bytes(code_dtype);
     // slot = [x chunk | codes chunk]; plus one shared workspace
-    const long long rows = std::min<long long>(round_up(N, 128), 1 << 16);
-    const size_t x_slot = static_cast<size_t>(rows) * cb->D * 4, c_slot = static_cast<size_t>(rows) * cb->L * cbytes;
-    const size_t ws_bytes = nat_rvq_workspace_bytes(cb, rows);
+    long long rows = 1 << 16;
+    { const char* e = getenv("NAT_HOST_CHUNK_ROWS"); if (e && atoll(e) >= 128) rows = round_up(atoll(e), 128); }
+    rows = std::min<long long>(round_up(N, 128), rows);
+    const size_t x_slot = static_cast<size_t>(rows) * D * 4, c_slot = static_cast<size_t>(rows) * L_total * cbytes;
+    const size_t ws_bytes = nat_rvq_stacks_workspace_bytes(stacks, n_stacks, rows);
     const size_t need = 2 * (round_up(x_slot, 256) + round_up(c_slot, 256)) + ws_bytes;
-    if (cb->host_arena_bytes < need) {
+    if (ctx->arena_bytes < need) {
         NAT_CUDA(cudaStreamSynchronize(st));
-        if (cb->host_arena_dev) NAT_CUDA(cudaFree(cb->host_arena_dev));
-        cb->host_arena_dev = nullptr; cb->host_arena_bytes = 0;
-        NAT_CUDA(cudaMalloc(&cb->host_arena_dev, need));
-        cb->host_arena_bytes = need;
+        NAT_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+        if (ctx->arena) NAT_CUDA(cudaFree(ctx->arena));
+        ctx->arena = nullptr; ctx->arena_bytes = 0;
+        NAT_CUDA(cudaMalloc(&ctx->arena, need));
+        ctx->arena_bytes = need;
     }
-    if (cb->copy_stream == nullptr) {
-        NAT_CUDA(cudaStreamCreateWithFlags(&cb->copy_stream, cudaStreamNonBlocking));
-        for (auto& e : cb->ev) NAT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    }
-    char* base = static_cast<char*>(cb->host_arena_dev);
+    char* base = static_cast<char*>(ctx->arena);
     float* xs[2]; char* cs[2];
     for (int s = 0; s < 2; ++s) { xs[s] = reinterpret_cast<float*>(base); base += round_up(x_slot, 256);
                                   cs[s] = base; base += round_up(c_slot, 256); }
     void* wsp = base;
-    // The BCT layout is strided per frame range, so it is staged with a 2-D copy per batch item; rows are contiguous.
+    const float* xin[nat::stack::MAX_STACKS];
     // copy stream: H2D(i) ; compute stream waits ev[s], encodes, D2H codes; copy stream waits ev[2+s] before reuse.
-    NAT_CUDA(cudaEventRecord(cb->ev[2], st)); NAT_CUDA(cudaEventRecord(cb->ev[3], st));
+    NAT_CUDA(cudaEventRecord(ctx->ev[2], st)); NAT_CUDA(cudaEventRecord(ctx->ev[3], st));
     int slot = 0;
-    if (layout == NAT_LAYOUT_ROWS) {
-        for (long long n0 = 0; n0 < N; n0 += rows, slot ^= 1) {
-            const long long n = std::min(rows, N - n0);
-            NAT_CUDA(cudaStreamWaitEvent(cb->copy_stream, cb->ev[2 + slot], 0));
-            NAT_CUDA(cudaMemcpyAsync(xs[slot], x_host + n0 * cb->D, static_cast<size_t>(n) * cb->D * 4,
-                                     cudaMemcpyHostToDevice, cb->copy_stream));
-            NAT_CUDA(cudaEventRecord(cb->ev[slot], cb->copy_stream));
-            NAT_CUDA(cudaStreamWaitEvent(st, cb->ev[slot], 0));
-            if (int rc = nat_rvq_encode_f32(cb, xs[slot], NAT_LAYOUT_ROWS, 1, n, cs[slot], code_dtype, nullptr, nullptr,
-                                            0.25f, nullptr, wsp, ws_bytes, NAT_RVQ_DEFAULT, st)) return rc;
-            NAT_CUDA(cudaMemcpy2DAsync(static_cast<char*>(codes_out_host) + n0 * cbytes, static_cast<size_t>(N) * cbytes,
-                                       cs[slot], static_cast<size_t>(n) * cbytes, static_cast<size_t>(n) * cbytes,
-                                       cb->L, cudaMemcpyDeviceToHost, st));
-            NAT_CUDA(cudaEventRecord(cb->ev[2 + slot], st));
-        }
-    } else {
-        // chunk along time inside each batch item: x[b, :, t0:t0+n] is D rows of n floats with pitch T
-        for (long long b = 0; b < B; ++b) {
-            for (long long t0 = 0; t0 < T; t0 += rows, slot ^= 1) {
-                const long long n = std::min(rows, T - t0);
-                NAT_CUDA(cudaStreamWaitEvent(cb->copy_stream, cb->ev[2 + slot], 0));
-                NAT_CUDA(cudaMemcpy2DAsync(xs[slot], static_cast<size_t>(n) * 4, x_host + (b * cb->D) * T + t0,
-                                           static_cast<size_t>(T) * 4, static_cast<size_t>(n) * 4, cb->D,
-                                           cudaMemcpyHostToDevice, cb->copy_stream));
-                NAT_CUDA(cudaEventRecord(cb->ev[slot], cb->copy_stream));
-                NAT_CUDA(cudaStreamWaitEvent(st, cb->ev[slot], 0));
-                if (int rc = nat_rvq_encode_f32(cb, xs[slot], NAT_LAYOUT_BCT, 1, n, cs[slot], code_dtype, nullptr,
-                                                nullptr, 0.25f, nullptr, wsp, ws_bytes, NAT_RVQ_DEFAULT, st)) return rc;
-                NAT_CUDA(cudaMemcpy2DAsync(static_cast<char*>(codes_out_host) + (b * T + t0) * cbytes,
-                                           static_cast<size_t>(N) * cbytes, cs[slot], static_cast<size_t>(n) * cbytes,
-                                           static_cast<size_t>(n) * cbytes, cb->L, cudaMemcpyDeviceToHost, st));
-                NAT_CUDA(cudaEventRecord(cb->ev[2 + slot], st));
-            }
+    // The BCT layout is strided per frame range, so it is staged with a 2-D copy per batch item; rows are contiguous.
+    const long long outer = layout == NAT_LAYOUT_ROWS ? 1 : B, inner = layout == NAT_LAYOUT_ROWS ? N : T;
+    for (long long b = 0; b < outer; ++b) {
+        for (long long t0 = 0; t0 < inner; t0 += rows, slot ^= 1) {
+            const long long n = std::min(rows, inner - t0);
+            NAT_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[2 + slot], 0));
+            if (layout == NAT_LAYOUT_ROWS)
+                NAT_CUDA(cudaMemcpyAsync(xs[slot], x_host + t0 * D, static_cast<size_t>(n) * D * 4, cudaMemcpyHostToDevice,
+                                         ctx->copy_stream));
+            else       // x[b, :, t0:t0+n] is D rows of n floats with pitch T
+                NAT_CUDA(cudaMemcpy2DAsync(xs[slot], static_cast<size_t>(n) * 4, x_host + (b * D) * T + t0,
+                                           static_cast<size_t>(T) * 4, static_cast<size_t>(n) * 4, D,
+                                           cudaMemcpyHostToDevice, ctx->copy_stream));
+            NAT_CUDA(cudaEventRecord(ctx->ev[slot], ctx->copy_stream));
+            NAT_CUDA(cudaStreamWaitEvent(st, ctx->ev[slot], 0));
+            for (int i = 0; i < n_stacks; ++i) xin[i] = xs[slot];
+            if (int rc = nat_rvq_encode_stacks_f32(stacks, n_stacks, xin, layout, 1, n, cs[slot], code_dtype, wsp, ws_bytes,
+                                                   NAT_RVQ_SINGLE_STREAM, st)) return rc;
+            NAT_CUDA(cudaMemcpy2DAsync(static_cast<char*>(codes_out_host) + (b * inner + t0) * cbytes,
+                                       static_cast<size_t>(N) * cbytes, cs[slot], static_cast<size_t>(n) * cbytes,
+                                       static_cast<size_t>(n) * cbytes, L_total, cudaMemcpyDeviceToHost, st));
+            NAT_CUDA(cudaEventRecord(ctx->ev[2 + slot], st));
         }
     }
     NAT_CUDA(cudaStreamSynchronize(st));     // host buffers are the caller's: results must have landed on return
     return NAT_OK;
+}
+
+// One stack, no caller context (kept from ABI 1): the handle's private context, one call at a time.
+int nat_rvq_encode_host_f32(const nat_rvq_codebooks* cb_const, const float* x_host, int layout, int64_t B, int64_t T,
+                            void* codes_out_host, int code_dtype, void* stream) {
+    nat_rvq_codebooks* cb = const_cast<nat_rvq_codebooks*>(cb_const);
+    if (cb == nullptr || x_host == nullptr || codes_out_host == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null argument");
+    std::lock_guard<std::mutex> lock(*cb->host_mutex);
+    if (cb->host_ctx == nullptr)
+        if (int rc = nat_host_ctx_create(&cb->host_ctx)) return rc;
+    const nat_rvq_codebooks* one[1] = {cb};
+    return nat_tokenize_host_f32(cb->host_ctx, one, 1, x_host, layout, B, T, codes_out_host, code_dtype, stream);
 }
 
 // ------------------------------------------------------------------------------------------------- front-end
@@ -922,9 +1209,13 @@ struct FePlan {
     float2* tw = nullptr;        // [NFFT/2]
     float* fbT = nullptr;        // [n_mels, NBINS] built-in HTK filterbank, band-major
     int2* band = nullptr;
-    float* fbT_user = nullptr;   // scratch for a caller-supplied filterbank
-    int2* band_user = nullptr;
     int sm_count = 148;
+    // cudaFuncAttributeMaxDynamicSharedMemorySize is per device: remembered per plan (plans are keyed by device)
+    std::atomic<size_t> mel_smem_set{0};
+    std::atomic<bool> spectral_smem_set{false};
+    FePlan() = default;
+    FePlan(const FePlan& o) : tw(o.tw), fbT(o.fbT), band(o.band), sm_count(o.sm_count),
+                              mel_smem_set(o.mel_smem_set.load()), spectral_smem_set(o.spectral_smem_set.load()) {}
 };
 
 std::mutex g_plan_mutex;
@@ -972,8 +1263,6 @@ int get_plan(int sample_rate, int n_mels, FePlan** out) {
         }
         NAT_CUDA(cudaMalloc(&plan.fbT, fbT.size() * 4));
         NAT_CUDA(cudaMalloc(&plan.band, sizeof(int2) * n_mels));
-        NAT_CUDA(cudaMalloc(&plan.fbT_user, fbT.size() * 4));
-        NAT_CUDA(cudaMalloc(&plan.band_user, sizeof(int2) * n_mels));
         NAT_CUDA(cudaMemcpy(plan.fbT, fbT.data(), fbT.size() * 4, cudaMemcpyHostToDevice));
         NAT_CUDA(cudaMemcpy(plan.band, band.data(), sizeof(int2) * n_mels, cudaMemcpyHostToDevice));
     }
@@ -1006,21 +1295,29 @@ int nat_mel_power_f32(const float* wave_dev, int64_t B, int64_t S, int sample_ra
     p.wave = wave_dev; p.S = S; p.T = nat_mel_num_frames(S, hop); p.hop = hop; p.n_mels = n_mels; p.tw = plan->tw;
     p.fbT = plan->fbT; p.band = plan->band; p.mel = mel_out_dev; p.logmel = logmel_out_dev;
     p.inv_wsum = 1.0f / (3.0f * fe::NFFT / 8.0f);                 // sum of hann^2 over a period = 3N/8
+    // A caller-supplied filterbank is converted to the banded form into scratch that belongs to THIS call
+    // (stream-ordered allocation): concurrent calls on different streams never share it.
+    char* fb_scratch = nullptr;
     if (fb_dev != nullptr) {
-        NAT_LAUNCH(7, st, fe::fb_to_banded_kernel<<<n_mels, 128, 0, st>>>(fb_dev, n_mels, plan->fbT_user, plan->band_user));
-        p.fbT = plan->fbT_user; p.band = plan->band_user;
+        const size_t fbt_bytes = static_cast<size_t>(round_up(static_cast<long long>(n_mels) * fe::NBINS * 4, 256));
+        NAT_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&fb_scratch), fbt_bytes + sizeof(int2) * n_mels, st));
+        float* fbT_user = reinterpret_cast<float*>(fb_scratch);
+        int2* band_user = reinterpret_cast<int2*>(fb_scratch + fbt_bytes);
+        NAT_LAUNCH(7, st, fe::fb_to_banded_kernel<<<n_mels, 128, 0, st>>>(fb_dev, n_mels, fbT_user, band_user));
+        p.fbT = fbT_user; p.band = band_user;
     }
     const long long groups_per_clip = (p.T + fe::FRAMES_PER_CTA - 1) / fe::FRAMES_PER_CTA;
     const long long total = groups_per_clip * B;
     const size_t smem = fe::mel_smem_bytes(n_mels);
-    static std::atomic<size_t> mel_smem_set{0};
-    if (mel_smem_set.load() < smem) {
+    if (plan->mel_smem_set.load() < smem) {
         NAT_CUDA(cudaFuncSetAttribute(fe::mel_power_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        mel_smem_set.store(smem);
+        plan->mel_smem_set.store(smem);
     }
     const int grid = static_cast<int>(std::min<long long>(total, plan->sm_count * 4LL * 4));
     NAT_LAUNCH(7, st, fe::mel_power_kernel<<<grid, fe::THREADS, smem, st>>>(p, groups_per_clip, total));
-    NAT_CUDA(cudaGetLastError());
+    const cudaError_t launch_err = cudaGetLastError();
+    if (fb_scratch != nullptr) cudaFreeAsync(fb_scratch, st);
+    NAT_CUDA(launch_err);
     return NAT_OK;
 }
 
@@ -1037,10 +1334,9 @@ int nat_spectral_stats_f32(const float* wave_dev, int64_t S, int sample_rate, in
     p.bin_hz = static_cast<float>(sample_rate) / fe::NFFT; p.tw = plan->tw; p.out = out_dev;
     const long long pairs = (p.T + 1) / 2;
     const size_t smem = fe::spectral_smem_bytes();
-    static std::atomic<bool> spectral_smem_set{false};
-    if (!spectral_smem_set.load()) {
+    if (!plan->spectral_smem_set.load()) {
         NAT_CUDA(cudaFuncSetAttribute(fe::spectral_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        spectral_smem_set.store(true);
+        plan->spectral_smem_set.store(true);
     }
     const int grid = static_cast<int>(std::min<long long>((pairs + 1) / 2, plan->sm_count * 4LL * 4));
     NAT_LAUNCH(7, static_cast<cudaStream_t>(stream), fe::spectral_stats_kernel<<<grid, fe::THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p));

@@ -75,7 +75,9 @@ __device__ __forceinline__ float4 make_rowinfo_bound(float sx, float lo2, float 
 __device__ __forceinline__ void finalize_row(const float4* r4, int dp4, float amax_lane,
                                              uint2* __restrict__ a_row, float4* __restrict__ rowinfo_out,
                                              const LayerConst* __restrict__ lc, int d_pad,
-                                             float* __restrict__ rowamax_out) {
+                                             float* __restrict__ rowamax_out,
+                                             float4* __restrict__ rowinfo_out_b = nullptr,
+                                             const LayerConst* __restrict__ lc_b = nullptr) {
     const int lane = threadIdx.x & 31;
     const float amax = warp_max(amax_lane);
     if (lane == 0 && rowamax_out != nullptr) *rowamax_out = amax;
@@ -102,7 +104,10 @@ __device__ __forceinline__ void finalize_row(const float4* r4, int dp4, float am
     lo2 = warp_sum(lo2);
     xt2 = warp_sum(xt2);
     xh2 = warp_sum(xh2);
-    if (lane == 0) *rowinfo_out = make_rowinfo(sx, lo2, xt2, xh2, lc, d_pad);
+    if (lane == 0) {
+        *rowinfo_out = make_rowinfo(sx, lo2, xt2, xh2, lc, d_pad);
+        if (rowinfo_out_b != nullptr) *rowinfo_out_b = make_rowinfo(sx, lo2, xt2, xh2, lc_b, d_pad);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------- layer 0 prep
@@ -110,7 +115,8 @@ __device__ __forceinline__ void finalize_row(const float4* r4, int dp4, float am
 __global__ void __launch_bounds__(256)
 prep_rows_kernel(const float* __restrict__ x, long long x_ld, int n, int D, int dp, float* __restrict__ r,
                  __half* __restrict__ a, float4* __restrict__ rowinfo, float* __restrict__ rowamax,
-                 const LayerConst* __restrict__ lc, bool in_place) {
+                 const LayerConst* __restrict__ lc, bool in_place,
+                 float4* __restrict__ rowinfo_b = nullptr, const LayerConst* __restrict__ lc_b = nullptr) {
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
@@ -133,7 +139,8 @@ prep_rows_kernel(const float* __restrict__ x, long long x_ld, int n, int D, int 
         }
         finalize_row(reinterpret_cast<const float4*>(rr), dp / 4, amax,
                      reinterpret_cast<uint2*>(a + static_cast<long long>(row) * dp), rowinfo + row, lc, dp,
-                     rowamax != nullptr ? rowamax + row : nullptr);
+                     rowamax != nullptr ? rowamax + row : nullptr,
+                     rowinfo_b != nullptr ? rowinfo_b + row : nullptr, lc_b);
     }
 }
 
@@ -145,7 +152,8 @@ constexpr int kPrepThreads = 512;                       // 16 warps: 2 CTAs of 9
 __global__ void __launch_bounds__(kPrepThreads)
 prep_bct_fused_kernel(const float* __restrict__ x, long long T, int D, long long n0, int n, int dp,
                       float* __restrict__ r, __half* __restrict__ a, float4* __restrict__ rowinfo,
-                      float* __restrict__ rowamax, const LayerConst* __restrict__ lc) {
+                      float* __restrict__ rowamax, const LayerConst* __restrict__ lc,
+                      float4* __restrict__ rowinfo_b = nullptr, const LayerConst* __restrict__ lc_b = nullptr) {
     extern __shared__ float s_tile[];                   // [32][dp + 1]
     constexpr int kWarps = kPrepThreads / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -198,6 +206,7 @@ prep_bct_fused_kernel(const float* __restrict__ x, long long T, int D, long long
         lo2 = warp_sum(lo2); xt2 = warp_sum(xt2); xh2 = warp_sum(xh2);
         if (lane == 0) {
             rowinfo[row] = make_rowinfo(sx, lo2, xt2, xh2, lc, dp);
+            if (rowinfo_b != nullptr) rowinfo_b[row] = make_rowinfo(sx, lo2, xt2, xh2, lc_b, dp);   // second stack, same frames
             if (rowamax != nullptr) rowamax[row] = amax;
         }
     }

@@ -71,9 +71,17 @@ def create_ndjson_stream(protocol, tokens: Dict, metadata: Dict = None, processi
     semantic_codes, acoustic_codes = tokens["semantic_codes"], tokens["acoustic_codes"]
     if semantic_codes and acoustic_codes and (len(semantic_codes) != st.num_semantic_layers or
                                               len(acoustic_codes) != st.num_acoustic_layers):
-        # the reference pads / truncates with a printed warning (nat.py:2731-2744); not worth a native path
-        raise ValueError(f"layer count mismatch: streams {len(semantic_codes)}+{len(acoustic_codes)}, protocol "
-                         f"{st.num_semantic_layers}+{st.num_acoustic_layers}")
+        # The reference pads / truncates every frame with a printed warning (nat.py:2731-2744) while its change
+        # detection still sees the unpadded lists: a malformed-input path, served by the reference's own method so
+        # that text and warnings stay what they were (no native form).
+        original = getattr(type(protocol), "_nat_b200_reference_create_ndjson_stream", None)
+        if original is None and getattr(type(protocol), "create_ndjson_stream", create_ndjson_stream) is not create_ndjson_stream:
+            original = type(protocol).create_ndjson_stream
+        if original is None:
+            raise ValueError(f"layer count mismatch: streams {len(semantic_codes)}+{len(acoustic_codes)}, protocol "
+                             f"{st.num_semantic_layers}+{st.num_acoustic_layers}, and the reference's own "
+                             "create_ndjson_stream is not reachable from this protocol object")
+        return original(protocol, tokens, metadata, processing_stats, duration_seconds, include_legend)
     lines = [st.create_header(duration_seconds, metadata, include_legend)]
     if semantic_codes and acoustic_codes:
         protocol.prev_semantic_tokens = None                 # same resets as nat.py:4476-4480
@@ -91,4 +99,7 @@ def create_ndjson_stream(protocol, tokens: Dict, metadata: Dict = None, processi
 
 def install(nat_module) -> None:
     """Rebind `StreamingProtocol.create_ndjson_stream` in the imported reference module."""
-    nat_module.StreamingProtocol.create_ndjson_stream = create_ndjson_stream
+    cls = nat_module.StreamingProtocol
+    if cls.create_ndjson_stream is not create_ndjson_stream:
+        cls._nat_b200_reference_create_ndjson_stream = cls.create_ndjson_stream      # malformed-input path, see above
+    cls.create_ndjson_stream = create_ndjson_stream

@@ -15,12 +15,17 @@ Contract: the tensor-core path implements the ARGMIN branch (nat.py:2155-2157). 
   * "philox": device-side noise, equal to the reference in distribution only (stated, never silent); distances from
     the tensor-core pass, bulk throughput. "philox_exact" keeps the exact per-frame scan with the same noise;
   * "delegate": call `stochastic_delegate` (e.g. the unmodified reference module).
-Training mode (EMA codebook updates, nat.py:2179-2181) always goes to `stochastic_delegate` or raises. The module
-never returns argmin codes when sampling was asked for. There is no CPU path: tensors must live on a CUDA device.
+Training mode (nat.py:2150, 2179-2181: the layer samples, then `_update_ema`) goes to `stochastic_delegate` when one
+is set; otherwise it runs here, layer by layer: native sampling on the device, then the EMA update of
+nat.py:2205-2221 in PyTorch on the same device (cold path; the codebook `copy_` it ends with bumps `_version`, so
+the next layer-call re-derives the device-side codebook state). The module never returns argmin codes when sampling
+was asked for. There is no CPU path: tensors must live on a CUDA device.
 """
 from __future__ import annotations
 
 import ctypes
+import inspect
+import types
 from typing import List, Optional, Sequence
 
 import torch
@@ -32,12 +37,21 @@ from . import _lib
 
 class _CodebookPack:
     """Owns the native `nat_rvq_codebooks` handle for a list of codebook tensors and refreshes it when any of them
-    is mutated in place (the host does `copy_` into them: nat.py:593, 1527, 2221) or moved."""
+    changed: detected from (data_ptr, `_version`, shape, device). `tensor.copy_()` bumps `_version`; writes through
+    `.data` (`codebook.data.copy_(...)`, nat.py:1926, 2073) do NOT, so every initializer of the drop-in calls
+    `invalidate()` afterwards, `ResidualVectorQuantizer.invalidate_codebooks()` is the public form for callers that
+    write through `.data` themselves, and `verify=True` compares the device contents on every call (one host sync)."""
 
     def __init__(self):
         self.handle = None
         self.signature = None
         self.device = None
+        self.verify = False          # compare contents with the uploaded snapshot on every get() (debugging aid)
+        self._snapshot = None
+
+    def invalidate(self):
+        """Forget what was uploaded: the next call re-derives the device-side codebook state."""
+        self.signature = None
 
     @staticmethod
     def _sig(codebooks: Sequence[torch.Tensor]):
@@ -47,7 +61,8 @@ class _CodebookPack:
         lib = _lib.load()
         sig = self._sig(codebooks)
         if self.handle is not None and sig == self.signature:
-            return self.handle
+            if not self.verify or all(torch.equal(a, b) for a, b in zip(self._snapshot, codebooks)):
+                return self.handle
         dev = codebooks[0].device
         K, D = codebooks[0].shape
         for cb in codebooks:
@@ -67,6 +82,7 @@ class _CodebookPack:
                 _lib.check(lib.nat_rvq_codebooks_create(ptrs, len(tensors), K, D, stream, ctypes.byref(out)))
                 self.handle = out
         self.signature, self.device = sig, dev
+        self._snapshot = [cb.detach().clone() for cb in codebooks] if self.verify else None
         return self.handle
 
     def close(self):
@@ -188,10 +204,16 @@ def _native_decode(pack: _CodebookPack, codebooks: Sequence[torch.Tensor], codes
     lib = _lib.load()
     dev = codebooks[0].device
     _require_cuda(codebooks[0], "codebook")
-    D = codebooks[0].shape[1]
+    K, D = codebooks[0].shape
     out = torch.empty((B, D, T), dtype=torch.float32, device=dev)
     if B * T == 0:
         return out
+    if n_lists:
+        # F.embedding raises IndexError on the reference path (nat.py:2195); an unchecked gather would read out of bounds
+        lo, hi = torch.aminmax(codes)
+        lo, hi = int(lo), int(hi)
+        if lo < 0 or hi >= K:
+            raise IndexError(f"code index out of range: codes span [{lo}, {hi}], the codebook has {K} entries")
     with torch.cuda.device(dev):
         handle = pack.get(codebooks)
         _lib.check(lib.nat_rvq_decode_f32(handle, codes.data_ptr() if n_lists else None, _lib.CODES_I64, n_lists, B, T,
@@ -225,6 +247,10 @@ class VectorQuantizer(nn.Module):
     def _argmin_mode(self) -> bool:
         return not (self.training or self.use_stochastic)
 
+    def invalidate_codebooks(self) -> None:
+        """Call after writing `codebook` through `.data` (which bypasses `_version`): the next call re-uploads."""
+        self._pack.invalidate()
+
     def forward(self, x):
         if x.dim() not in [2, 3]:
             raise ValueError(f"VectorQuantizer expects 2D or 3D input, got {x.dim()}D tensor with shape {x.shape}")
@@ -235,16 +261,18 @@ class VectorQuantizer(nn.Module):
         if C != self.input_dim:
             raise ValueError(f"Expected {self.input_dim} feature dimensions, got {C}")
         if not self._argmin_mode():
-            if self.training or self.sampling_mode == "delegate":
-                if self.stochastic_delegate is not None:
-                    return self.stochastic_delegate(x if len(original_shape) == 3 else x.squeeze(0))
+            if self.stochastic_delegate is not None and (self.training or self.sampling_mode == "delegate"):
+                return self.stochastic_delegate(x if len(original_shape) == 3 else x.squeeze(0))
+            if self.sampling_mode == "delegate":
                 raise NotImplementedError(
-                    "VectorQuantizer: training=%s, sampling_mode=%r: training (EMA updates, nat.py:2179-2181) and "
-                    "delegated sampling need `stochastic_delegate`; eval-mode sampling runs natively with "
-                    "sampling_mode 'host_noise' or 'philox'." % (self.training, self.sampling_mode))
+                    "VectorQuantizer: sampling_mode='delegate' needs `stochastic_delegate` (e.g. the reference module); "
+                    "sampling runs natively with sampling_mode 'host_noise' or 'philox'.")
             codes, quantized, loss = _native_sample(self._pack, [self.codebook], x, self.commitment_weight, True, True,
                                                     [self.temperature], self.sampling_mode, self._draws)
             self._draws += 1
+            if self.training:                                   # nat.py:2179-2181
+                flat_input = x.transpose(1, 2).contiguous().view(-1, self.input_dim)
+                self._update_ema(flat_input, codes[0].reshape(-1))
         else:
             codes, quantized, loss = _native_encode(self._pack, [self.codebook], x, self.commitment_weight, True, True,
                                                     exact_scan=self.exact_scan)
@@ -267,7 +295,8 @@ class VectorQuantizer(nn.Module):
         return quantized
 
     def _update_ema(self, flat_input, codes_flat):
-        """EMA codebook update (nat.py:2205-2221); training-only, never on the tokenise path, kept in PyTorch."""
+        """EMA codebook update (nat.py:2205-2221), called by the training-mode forward; never on the tokenise path,
+        kept in PyTorch. `codebook.copy_` bumps `_version`: the device-side codebook state follows."""
         with torch.no_grad():
             onehot = F.one_hot(codes_flat, self.codebook_size).float()
             self.ema_count.mul_(self.ema_decay).add_(onehot.sum(dim=0), alpha=1 - self.ema_decay)
@@ -300,6 +329,52 @@ class ResidualVectorQuantizer(nn.Module):
         self.last_stats = None
         self._pack = _CodebookPack()
 
+    # -- codebook sourcing (cold path, stays with the reference) -------------------------------------------------
+    # The reference fills the codebooks on the first forward of the tokenizer through methods of ITS quantizer class
+    # (`initialize_from_mert_model` / `initialize_from_encodec_weights` / `initialize_from_encodec`, called at
+    # nat.py:3075, 3086, 3166, 3176) and their helpers (`_validate_*`, `_prepare_encodec_features`). Those only touch
+    # `self.quantizers[i].codebook / ema_*`, `self.input_dim`, `self.codebook_size`, `self.num_quantizers`, all of
+    # which this class keeps, so they are run unmodified on the drop-in: `install()` / `patch_reference_module()`
+    # record the reference class here and unknown attributes resolve to its functions bound to this object. The
+    # initializers write through `.data` (nat.py:1926, 2073), which `_version` does not see: they are wrapped to
+    # invalidate the device-side codebook state when they return.
+    _reference_class = None
+    _INITIALIZERS = ("initialize_from_mert_model", "initialize_from_encodec_weights", "initialize_from_encodec")
+
+    def __getattr__(self, name):
+        try:
+            return super().__getattr__(name)
+        except AttributeError:
+            ref = self.__dict__.get("_reference_class") or type(self)._reference_class
+            if ref is None or name.startswith("__") or not hasattr(ref, name):
+                if name in self._INITIALIZERS:
+                    raise RuntimeError(
+                        f"{name}: codebook sourcing stays with the reference implementation (SURVEY.md L1b); graft this "
+                        "module with install() / patch_reference_module() so that its class is known, or fill "
+                        "`quantizers[i].codebook` yourself and call invalidate_codebooks()") from None
+                raise
+            static = inspect.getattr_static(ref, name)
+            fn = getattr(ref, name)
+            if isinstance(static, staticmethod) or not callable(fn):
+                return fn
+            bound = types.MethodType(fn, self)
+            if name not in self._INITIALIZERS:
+                return bound
+
+            def initializer(*args, **kwargs):
+                try:
+                    return bound(*args, **kwargs)
+                finally:
+                    self.invalidate_codebooks()
+            return initializer
+
+    def invalidate_codebooks(self) -> None:
+        """Call after writing codebooks through `.data` (which bypasses `_version`): the next call re-uploads."""
+        self._pack.invalidate()
+        for q in self.quantizers:
+            if isinstance(q, VectorQuantizer):
+                q._pack.invalidate()
+
     # -- helpers ---------------------------------------------------------------------------------------------
     def _codebooks(self) -> List[torch.Tensor]:
         return [q.codebook for q in self.quantizers]
@@ -309,7 +384,24 @@ class ResidualVectorQuantizer(nn.Module):
                    for q in self.quantizers)
 
     def _needs_delegate(self) -> bool:
-        return self.sampling_mode == "delegate" or any(q.training for q in self.quantizers)
+        return self.sampling_mode == "delegate"
+
+    def _training(self) -> bool:
+        return any(q.training for q in self.quantizers)
+
+    def _forward_training(self, x):
+        """The layer loop of nat.py:1393-1415 with every layer in training mode: sample, update the layer's EMA
+        statistics and codebook, subtract. One native call per layer (the codebooks change between layers' calls)."""
+        residual = x
+        quantized_layers, codes = [], []
+        total_loss = 0
+        for quantizer in self.quantizers:
+            quantized, code, loss = quantizer(residual)
+            quantized_layers.append(quantized)
+            codes.append(code.cpu() if self.codes_on_cpu else code)
+            total_loss = total_loss + loss
+            residual = residual - quantized.detach()
+        return sum(quantized_layers), codes, {"vq_loss": total_loss, "num_layers": len(quantized_layers)}
 
     def _sample(self, x, want_quantized: bool, want_loss: bool):
         temps = [float(q.temperature) if q.use_stochastic else 0.0 for q in self.quantizers]
@@ -347,14 +439,18 @@ class ResidualVectorQuantizer(nn.Module):
         try:
             x = self._validate(x)
             if not self._argmin_mode():
+                if self.stochastic_delegate is not None and (self._needs_delegate() or self._training()):
+                    return self.stochastic_delegate(x)
                 if self._needs_delegate():
-                    if self.stochastic_delegate is not None:
-                        return self.stochastic_delegate(x)
                     raise NotImplementedError(
-                        "ResidualVectorQuantizer: a layer is in training mode or sampling_mode is 'delegate', and no "
-                        "`stochastic_delegate` (the reference module) was supplied. Eval-mode sampling runs natively "
-                        "with sampling_mode 'host_noise' or 'philox'; install(tokenizer, force_argmin=True) gives the "
-                        "argmin contract (nat.py:2155-2157).")
+                        "ResidualVectorQuantizer: sampling_mode is 'delegate' and no `stochastic_delegate` (the "
+                        "reference module) was supplied. Sampling runs natively with sampling_mode 'host_noise' or "
+                        "'philox'; install(tokenizer, force_argmin=True) gives the argmin contract (nat.py:2155-2157).")
+                if self._training():
+                    for q in self.quantizers:           # layers sample with the stack's noise source
+                        if isinstance(q, VectorQuantizer):
+                            q.sampling_mode = self.sampling_mode
+                    return self._forward_training(x)
                 codes, quantized, loss = self._sample(x, True, True)
             else:
                 stats = self._stats_tensor(x.device)

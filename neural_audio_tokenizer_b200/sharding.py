@@ -44,3 +44,64 @@ def all_gather_codes(local_codes: torch.Tensor, n_total: int, group=None) -> tor
     dist.all_gather_into_tensor(recv.view(torch.uint8).view(-1), send.view(torch.uint8).view(-1), group=group)
     # [world, L, per] -> [L, world * per] -> drop the padding of the last shards
     return recv.permute(1, 0, 2).reshape(L, world * per)[:, :n_total].contiguous()
+
+
+class CodeGatherer:
+    """Overlapped form of `all_gather_codes` for a loop of encode steps: the exchange of step i runs on a side stream
+    under the kernels of step i + 1.
+
+    Per step, on the caller's stream: a copy of the rank's [L, n_local] index streams into one of two staging buffers
+    (a few MB; the encode kernels may then overwrite their output at once). On the side stream: one
+    `all_gather_into_tensor` of the staging buffer as bytes (NCCL has no 16-bit integer type) and one strided copy
+    that lays the [world, L, per] blocks out as [L, world * per], the layout the consumers index. `wait()` makes the
+    caller's stream wait for everything outstanding; `all_gather` returns the output tensor of this step (valid after
+    `wait()` or after the next-but-one call). Shards are padded to the common ceil size."""
+
+    def __init__(self, n_layers: int, n_local: int, world: int, device, n_total: int = None, group=None):
+        self.L, self.world, self.group = n_layers, world, group
+        self.n_total = n_total if n_total is not None else n_local * world
+        self.per = -(-self.n_total // world)
+        self.n_local = n_local
+        self.on_gpu = torch.device(device).type == "cuda"    # host tensors (gloo, the CPU tests): same plumbing, in order
+        self.comm = torch.cuda.Stream(device=device) if self.on_gpu else None
+        self.send = [torch.zeros((n_layers, self.per), dtype=torch.int16, device=device) for _ in range(2)]
+        self.recv = [torch.empty((world, n_layers, self.per), dtype=torch.int16, device=device) for _ in range(2)]
+        self.out = [torch.empty((n_layers, world * self.per), dtype=torch.int16, device=device) for _ in range(2)]
+        self.staged = [torch.cuda.Event() for _ in range(2)] if self.on_gpu else None
+        self.done = [torch.cuda.Event() for _ in range(2)] if self.on_gpu else None
+        self.used = [False, False]
+        self.i = 0
+
+    def all_gather(self, local_codes: torch.Tensor) -> torch.Tensor:
+        if tuple(local_codes.shape) != (self.L, self.n_local):
+            raise ValueError(f"expected [{self.L}, {self.n_local}] index streams, got {tuple(local_codes.shape)}")
+        k = self.i & 1
+        self.i += 1
+        result = self.out[k][:, :self.n_total] if self.world * self.per != self.n_total else self.out[k]
+        if not self.on_gpu:
+            self.send[k][:, :self.n_local].copy_(local_codes)
+            dist.all_gather_into_tensor(self.recv[k].view(torch.uint8).view(-1), self.send[k].view(torch.uint8).view(-1),
+                                        group=self.group)
+            self.out[k].view(self.L, self.world, self.per).copy_(self.recv[k].permute(1, 0, 2))
+            return result
+        cur = torch.cuda.current_stream(local_codes.device)
+        if self.used[k]:
+            cur.wait_event(self.done[k])                    # the exchange that last used this slot (two steps ago)
+        self.send[k][:, :self.n_local].copy_(local_codes)
+        self.staged[k].record(cur)
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(self.staged[k])
+            dist.all_gather_into_tensor(self.recv[k].view(torch.uint8).view(-1), self.send[k].view(torch.uint8).view(-1),
+                                        group=self.group)
+            self.out[k].view(self.L, self.world, self.per).copy_(self.recv[k].permute(1, 0, 2))
+            self.done[k].record(self.comm)
+        self.used[k] = True
+        return result
+
+    def wait(self) -> None:
+        if not self.on_gpu:
+            return
+        cur = torch.cuda.current_stream(self.send[0].device)
+        for k in range(2):
+            if self.used[k]:
+                cur.wait_event(self.done[k])

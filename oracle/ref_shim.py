@@ -1,8 +1,10 @@
 """Import the UNMODIFIED reference (`/root/reference/neural_audio_tokenizer.py`) in the authoring container.
 
-TEST INFRASTRUCTURE ONLY.  Used by `oracle/make_golden.py` (to mint golden vectors) and by the
-container-only cross-check tests (skipped when `/root/reference` is absent, i.e. on the GPU box).
-Nothing in the product package, in `bench.py`, in `smoke()` or in the `-m gpu` tests imports this.
+TEST INFRASTRUCTURE ONLY.  Used by `oracle/make_golden.py` (to mint golden vectors), by the cross-check tests, by
+the config-1 GPU test (the reference pipeline with the drop-in installed) and by `bench.py --impl reference` / its
+`cpu_baseline` leg (the unmodified reference timed on the host cores).  Nothing in the product package imports
+this.  On the GPU box `/root/reference` does not exist: the git-ignored copy `baseline/_ref/` that
+`__graft_entry__.build()` makes in the authoring container travels with the gpurun snapshot and is found here.
 
 The reference imports `librosa` and `soundfile` unconditionally (nat.py:108-110); neither is installed
 here.  The recipe is: touch the transformers symbols first, then register stub
@@ -16,11 +18,40 @@ import sys
 import tempfile
 import types
 
-REFERENCE_DIR = os.environ.get("NAT_REFERENCE_DIR", "/root/reference")
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CARRIED_DIR = os.path.join(_ROOT, "baseline", "_ref")      # git-ignored copy that travels to the GPU box (see carry_reference)
+
+
+def _find_reference_dir() -> str:
+    """NAT_REFERENCE_DIR, then the mounted reference (authoring container), then the carried copy (GPU box)."""
+    cands = [os.environ.get("NAT_REFERENCE_DIR"), "/root/reference", CARRIED_DIR]
+    for d in cands:
+        if d and os.path.isfile(os.path.join(d, "neural_audio_tokenizer.py")):
+            return d
+    return cands[0] or "/root/reference"
+
+
+REFERENCE_DIR = _find_reference_dir()
 
 
 def reference_available() -> bool:
     return os.path.isfile(os.path.join(REFERENCE_DIR, "neural_audio_tokenizer.py"))
+
+
+def carry_reference(src: str = "/root/reference") -> bool:
+    """Copy the unmodified reference file and its test clips into the git-ignored `baseline/_ref/` so that the
+    reference arm of bench.py and the config-1 GPU test can run on the GPU box, where /root/reference does not exist
+    (SURVEY.md section 7). Nothing is copied into the tracked tree. Returns True when the carried copy is present."""
+    import shutil
+    names = ["neural_audio_tokenizer.py", "test_simple.wav", "test_simple2.wav", "test.wav", "LICENSE"]
+    if os.path.isfile(os.path.join(src, names[0])) and os.path.abspath(src) != os.path.abspath(CARRIED_DIR):
+        os.makedirs(CARRIED_DIR, exist_ok=True)
+        for n in names:
+            a, b = os.path.join(src, n), os.path.join(CARRIED_DIR, n)
+            if os.path.isfile(a) and (not os.path.isfile(b) or os.path.getmtime(a) > os.path.getmtime(b)
+                                      or os.path.getsize(a) != os.path.getsize(b)):
+                shutil.copy2(a, b)
+    return os.path.isfile(os.path.join(CARRIED_DIR, names[0]))
 
 
 def _stub(name: str) -> types.ModuleType:

@@ -223,3 +223,37 @@ def classify_sampling_mismatches(codes_ref: np.ndarray, codes_test: np.ndarray, 
         out["flips"].append({"frame": int(n), "layer": first, "ref": int(codes_ref[first, n]),
                              "test": int(codes_test[first, n]), "rel_gap": float(gap), "kind": kind})
     return out
+
+
+# ------------------------------------------------------------------------------------------------ training mode
+def ema_update(codebook: torch.Tensor, ema_count: torch.Tensor, ema_weight: torch.Tensor, flat_input: torch.Tensor,
+               codes_flat: torch.Tensor, ema_decay: float = 0.99) -> None:
+    """`VectorQuantizer._update_ema` (nat.py:2205-2221), in place on the three buffers."""
+    with torch.no_grad():
+        onehot = F.one_hot(codes_flat, codebook.shape[0]).float()
+        ema_count.mul_(ema_decay).add_(onehot.sum(dim=0), alpha=1 - ema_decay)
+        ema_weight.mul_(ema_decay).add_(torch.matmul(onehot.t(), flat_input), alpha=1 - ema_decay)
+        codebook.copy_(ema_weight / (ema_count + 1e-5).unsqueeze(1))
+
+
+def rvq_forward_training(x: torch.Tensor, codebooks: Sequence[torch.Tensor], ema_counts: Sequence[torch.Tensor],
+                         ema_weights: Sequence[torch.Tensor], temperature: float = 0.5, commitment_weight: float = 0.25,
+                         ema_decay: float = 0.99, generator: torch.Generator = None):
+    """The layer loop of nat.py:1393-1415 with every layer in training mode (nat.py:2150: a training layer samples
+    whatever `use_stochastic` says; nat.py:2179-2181: then the EMA update). Mutates the buffers in place like the
+    reference. Returns (final, codes, losses)."""
+    x = _as_bct(x, codebooks[0].shape[1])
+    with torch.no_grad():
+        residual = x
+        layers, codes = [], []
+        total = 0
+        for cb, cnt, wgt in zip(codebooks, ema_counts, ema_weights):
+            quantized, code, loss, _, _ = vq_layer_sampling(residual, cb, temperature, commitment_weight, generator)
+            flat = residual.transpose(1, 2).contiguous().view(-1, cb.shape[1])
+            ema_update(cb, cnt, wgt, flat, code.reshape(-1), ema_decay)
+            layers.append(quantized)
+            codes.append(code)
+            total = total + loss
+            residual = residual - quantized
+        final = sum(layers)
+    return final, codes, {"vq_loss": total, "num_layers": len(layers)}

@@ -17,15 +17,18 @@ for K in [int(k) for k in os.environ.get("PROBE_KS", "1024,4096").split(",")]:
     h = rvq._pack.get(rvq._codebooks())
     wsb = lib.nat_rvq_workspace_bytes(h, N); ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
     codes = torch.empty((4, N), dtype=torch.int16, device="cuda")
-    for group in os.environ.get("PROBE_GROUPS", "3").split(","):
+    for group, mask in [(g, m) for g in os.environ.get("PROBE_GROUPS", "3").split(",") for m in os.environ.get("PROBE_MASKS", "").split(",")]:
         os.environ["NAT_RVQ_GROUP"] = group
+        if mask:
+            os.environ["NAT_RVQ_STORE_MASK_SET"] = mask
+            group = f"{group} store_mask={mask}"
         os.environ["NAT_RVQ_DBG_MODE"] = "0"
         prof = (ctypes.c_float * 8)()
         best = 1e9
         for rep in range(5):
             _lib.check(lib.nat_rvq_encode_profile_f32(h, x.data_ptr(), 0, 1, N, codes.data_ptr(), 2, None, None, 0.25, None, ws.data_ptr(), wsb, 2, st, prof))
             if rep: best = min(best, prof[1])
-        print(f"K={K} group={group} PRODUCTION stack_ms={best:.3f} prep_ms={prof[0]:.3f}", flush=True)
+        print(f"K={K} group={group} PRODUCTION stack_ms={best:.3f} prep_ms={prof[0]:.3f} checksum={int(codes.long().sum())}", flush=True)
         for mode in os.environ.get("PROBE_MODES", "0,3,6,7,16,19").split(","):
             os.environ["NAT_RVQ_DBG_MODE"] = mode
             nc, ns = ctypes.c_int(), ctypes.c_int()

@@ -32,7 +32,7 @@ def test_header_symbols_are_exported_and_bound(lib):
 
 def test_abi_version_and_pure_host_helpers(lib):
     handle = lib.load()
-    assert handle.nat_abi_version() == 1
+    assert handle.nat_abi_version() == 2
     assert handle.nat_mel_num_frames(22050, 512) == 44                 # 1 + S // hop (center=True)
     assert handle.nat_mel_num_frames(24000 * 3600, 320) == 270001
     assert handle.nat_spectral_num_frames(22050, 2048, 512) == 40      # nat.py:2400-2403

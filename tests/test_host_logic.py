@@ -62,7 +62,7 @@ def test_sampling_modes_never_fall_through_to_argmin():
     for q in rvq.quantizers:
         q.use_stochastic = False
     rvq.train()
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="no CPU fallback"):            # training samples + EMA natively: device only
         rvq(torch.randn(1, 8, 4))
     calls = []
 
@@ -76,9 +76,46 @@ def test_sampling_modes_never_fall_through_to_argmin():
     rvq.eval()
     rvq.stochastic_delegate = None
     assert rvq.training is False
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
         rvq(torch.randn(1, 8, 4), training_mode=True)
     assert rvq.training is False                                          # restored in finally, nat.py:1417-1420
+
+
+def test_codebook_initializers_run_the_reference_code_and_invalidate():
+    """The tokenizer calls `initialize_from_mert_model` & co. on its quantizers (nat.py:3075-3176); on the drop-in they
+    resolve to the reference class's own functions, and their `.data` writes (which `_version` does not see)
+    invalidate the uploaded codebook state."""
+    class FakeReferenceRVQ:
+        def initialize_from_mert_model(self, model_name="m", **kw):
+            for i, q in enumerate(self.quantizers):
+                q.codebook.data.copy_(torch.full_like(q.codebook, float(i + 1)))      # nat.py:1926 writes through .data
+            return self._helper(model_name)
+
+        def _helper(self, name):
+            return f"{name}:{self.codebook_size}x{self.input_dim}"
+
+        @staticmethod
+        def _static(a):
+            return a + 1
+
+    rvq = ResidualVectorQuantizer(8, 16, 2, use_stochastic=False).eval()
+    with pytest.raises(RuntimeError, match="codebook sourcing stays with the reference"):
+        rvq.initialize_from_mert_model(model_name="x")
+    with pytest.raises(AttributeError):
+        rvq.no_such_thing
+    rvq._reference_class = FakeReferenceRVQ
+    rvq._pack.signature = ("uploaded",)
+    for q in rvq.quantizers:
+        q._pack.signature = ("uploaded",)
+    v0 = rvq.quantizers[0].codebook._version
+    assert rvq.initialize_from_mert_model(model_name="mert") == "mert:16x8"
+    assert rvq.quantizers[0].codebook._version == v0                      # .data.copy_ leaves the version alone ...
+    assert rvq._pack.signature is None and all(q._pack.signature is None for q in rvq.quantizers)   # ... hence this
+    assert float(rvq.quantizers[1].codebook[0, 0]) == 2.0
+    assert rvq._static(1) == 2
+    rvq._pack.signature = ("uploaded",)
+    rvq.invalidate_codebooks()
+    assert rvq._pack.signature is None
 
 
 def test_no_cpu_fallback():

@@ -146,3 +146,38 @@ def test_native_ndjson_stream_equals_live_reference(nat, rle):
     got = nd.create_ndjson_stream(nat.StreamingProtocol(**kw), tokens, metadata={"k": 1}, processing_stats={"n": n},
                                   duration_seconds=n * 512 / 22050)
     assert got == want
+
+
+def test_ndjson_layer_count_mismatch_behaves_like_the_reference(nat, capsys):
+    """Fewer / more code streams than the protocol's layer count: the reference pads or truncates each frame with a
+    printed warning (nat.py:2731-2744); the drop-in hands that malformed-input case to the reference's own method."""
+    from neural_audio_tokenizer_b200 import ndjson as nd
+    rng = np.random.default_rng(5)
+    sem = [torch.from_numpy(rng.integers(0, 64, 20))[None] for _ in range(3)]      # protocol expects 4 + 4
+    ac = [torch.from_numpy(rng.integers(0, 64, 20))[None] for _ in range(5)]
+    tokens = {"semantic_codes": sem, "acoustic_codes": ac}
+    kw = dict(sample_rate=22050, hop_length=512, rle_mode=False, codebook_size=64)
+    want = nat.StreamingProtocol(**kw).create_ndjson_stream(tokens)
+    warned = capsys.readouterr().err                       # the reference redirects print to stderr (nat.py:161-455)
+    got = nd.create_ndjson_stream(nat.StreamingProtocol(**kw), tokens)
+    assert got == want and capsys.readouterr().err == warned and "Warning: Expected 4 semantic tokens" in warned
+
+
+def test_oracle_training_forward_is_bit_identical_to_reference(nat):
+    """Training mode: every layer samples and then updates its EMA statistics and codebook (nat.py:2150, 2179-2181,
+    2205-2221). The oracle restatement must leave the same codes and the same buffers behind."""
+    torch.manual_seed(11)
+    rvq = nat.ResidualVectorQuantizer(16, 32, 3).train()
+    cbs = [q.codebook.clone() for q in rvq.quantizers]
+    cnt = [q.ema_count.clone() for q in rvq.quantizers]
+    wgt = [q.ema_weight.clone() for q in rvq.quantizers]
+    x = torch.randn(2, 16, 40, generator=torch.Generator().manual_seed(12))
+    torch.manual_seed(99)
+    q_ref, codes_ref, losses_ref = rvq(x)
+    torch.manual_seed(99)
+    q, codes, losses = rvq_oracle.rvq_forward_training(x, cbs, cnt, wgt)
+    assert torch.equal(q, q_ref.detach()) and float(losses["vq_loss"]) == float(losses_ref["vq_loss"])
+    for a, b in zip(codes, codes_ref):
+        assert torch.equal(a, b)
+    for l, ql in enumerate(rvq.quantizers):
+        assert torch.equal(cbs[l], ql.codebook) and torch.equal(cnt[l], ql.ema_count) and torch.equal(wgt[l], ql.ema_weight)

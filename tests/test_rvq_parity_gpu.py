@@ -231,6 +231,34 @@ def test_vector_quantizer_single_layer_and_2d_input():
     np.testing.assert_array_equal(codes2.cpu().numpy(), rvq_oracle.vq_layer(x, cbs[1])[1].numpy())
 
 
+def test_training_forward_samples_and_updates_ema_like_the_reference():
+    """training_mode=True: every layer samples (nat.py:2150) and then runs `_update_ema` (nat.py:2179-2181,
+    2205-2221) before the next layer sees the residual. Host-drawn noise from a seeded generator reproduces the
+    restated reference chain: codes equal, quantised sum equal, EMA buffers and codebooks equal up to the fp32
+    summation order of the one-hot matmul (device GEMM vs MKL)."""
+    from neural_audio_tokenizer_b200 import ResidualVectorQuantizer
+    torch.manual_seed(21)
+    rvq = ResidualVectorQuantizer(16, 32, 3)
+    cbs = [q.codebook.clone() for q in rvq.quantizers]
+    cnt = [q.ema_count.clone() for q in rvq.quantizers]
+    wgt = [q.ema_weight.clone() for q in rvq.quantizers]
+    x = torch.randn(2, 16, 40, generator=torch.Generator().manual_seed(22))
+    rvq = rvq.cuda().eval()
+    torch.manual_seed(77)
+    q_dev, codes_dev, losses_dev = rvq(x.cuda(), training_mode=True)
+    assert not rvq.training
+    torch.manual_seed(77)
+    q_ref, codes_ref, losses_ref = rvq_oracle.rvq_forward_training(x, cbs, cnt, wgt)
+    for a, b in zip(codes_dev, codes_ref):
+        np.testing.assert_array_equal(a.cpu().numpy(), b.numpy())
+    assert torch.allclose(q_dev.cpu(), q_ref, rtol=1e-5, atol=1e-5)
+    assert abs(losses_dev["vq_loss"].item() - float(losses_ref["vq_loss"])) <= 1e-4 * float(losses_ref["vq_loss"])
+    for l, ql in enumerate(rvq.quantizers):
+        assert torch.allclose(ql.codebook.cpu(), cbs[l], rtol=1e-5, atol=1e-5)
+        assert torch.allclose(ql.ema_count.cpu(), cnt[l], rtol=1e-6, atol=1e-6)
+        assert torch.allclose(ql.ema_weight.cpu(), wgt[l], rtol=1e-5, atol=1e-5)
+
+
 def test_errors_and_modes():
     from neural_audio_tokenizer_b200 import ResidualVectorQuantizer
     rvq = ResidualVectorQuantizer(32, 64, 2).cuda().eval()           # reference default: use_stochastic=True
@@ -243,9 +271,8 @@ def test_errors_and_modes():
     rvq.sampling_mode = "host_noise"
     for q in rvq.quantizers:
         q.use_stochastic = False
-    with pytest.raises(NotImplementedError):
-        rvq(x, training_mode=True)
-    assert not rvq.training
+    out = rvq(x, training_mode=True)                                  # training runs natively too (next test)
+    assert len(out) == 3 and len(out[1]) == 2 and not rvq.training
     with pytest.raises(ValueError):
         rvq(torch.randn(32, device="cuda"))
     with pytest.raises(ValueError):

@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from neural_audio_tokenizer_b200.sharding import all_gather_codes, shard_range
+from neural_audio_tokenizer_b200.sharding import CodeGatherer, all_gather_codes, shard_range
 from oracle import rvq_oracle
 
 
@@ -38,6 +38,12 @@ def _worker(rank, world, port, n_frames, out_dir):
         local_codes = torch.stack([c[0] for c in sem + ac])          # [8, n_local]
         full = all_gather_codes(local_codes, n_frames)
         assert full.dtype == torch.int16 and full.shape == (8, n_frames)
+        # the per-step gatherer bench.py uses (side stream on the GPU, in order here): same layout, twice in a row
+        g = CodeGatherer(8, stop - start, world, "cpu", n_total=n_frames)
+        for _ in range(3):
+            again = g.all_gather(local_codes.to(torch.int16))
+            g.wait()
+            assert torch.equal(again, full)
         np.save(os.path.join(out_dir, f"rank{rank}.npy"), full.numpy())
     finally:
         dist.destroy_process_group()
