@@ -202,6 +202,16 @@ int nat_tokenize_host_f32(nat_host_ctx* ctx, const nat_rvq_codebooks* const* sta
 int nat_mel_power_f32(const float* wave_dev, int64_t B, int64_t S, int sample_rate, int n_fft, int hop, int n_mels,
                       const float* fb_dev, float* mel_out_dev, float* logmel_out_dev, void* stream);
 
+/* The same transform with the filterbank prepared once (what the MelSpectrogram drop-in does: its filterbank is a
+ * constant of the object): nat_mel_filterbank_prepare turns a dense [n_fft/2+1, n_mels] filterbank into the banded
+ * form the kernel reads (nat_mel_filterbank_bytes(n_mels) bytes of device memory owned by the caller). The dense
+ * fb_dev of nat_mel_power_f32 is converted on every call into stream-ordered scratch instead. */
+size_t nat_mel_filterbank_bytes(int n_mels);
+int nat_mel_filterbank_prepare(const float* fb_dev, int n_mels, void* banded_out_dev, void* stream);
+int nat_mel_power_banded_f32(const float* wave_dev, int64_t B, int64_t S, int sample_rate, int n_fft, int hop,
+                             int n_mels, const void* fb_banded_dev, float* mel_out_dev, float* logmel_out_dev,
+                             void* stream);
+
 /* Spectral centroid and bandwidth per frame. Replaces the STFT loop of SemanticAudioEncoder._spectral_fallback
  * (nat.py:2395-2433): frames = 1 + (S - n_fft)/hop (1 when S < n_fft), no centring, zero-padded tail.
  *   wave_dev [S] fp32;  out_dev [2, T] fp32 (row 0 centroid, row 1 bandwidth). */

@@ -52,6 +52,10 @@ _SIGNATURES = [
                                       c_int, c_void_p]),
     ("nat_mel_power_f32", c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                   c_void_p, c_void_p]),
+    ("nat_mel_filterbank_bytes", c_size_t, [c_int]),
+    ("nat_mel_filterbank_prepare", c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    ("nat_mel_power_banded_f32", c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                         c_void_p, c_void_p]),
     ("nat_spectral_stats_f32", c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
     ("nat_mel_num_frames", c_int64, [c_int64, c_int]),
     ("nat_spectral_num_frames", c_int64, [c_int64, c_int, c_int]),

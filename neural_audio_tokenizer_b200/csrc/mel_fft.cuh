@@ -8,8 +8,13 @@
 // Two real frames share one complex FFT (frame a in the real lane, frame b in the imaginary lane) and are separated
 // afterwards with the conjugate-symmetry identities. The transform is a three-pass decimation-in-frequency
 // 2048 = 16 x 16 x 8 by a team of 128 threads with 16 points per thread in registers: pass 1 reads the windowed
-// samples straight from global memory, passes 2 and 3 exchange through a padded, bank-conflict-free 19 KB shared
-// buffer; the spectrum is left in digit-reversed order and the epilogue indexes it through fft_pos().
+// samples straight from global memory, passes 2 and 3 exchange through a padded 17 KB shared buffer; the spectrum
+// ends up in natural order with one pad per 16 elements (fft_pos).
+// Every shared-memory access of the transform is an 8-byte complex element, served per half-warp: one pad per 16
+// elements makes all five exchange patterns (pass-1 store, pass-2 load / store, pass-3 load / store) hit 16 distinct
+// bank pairs, and the twiddles come from tables laid out by (k, thread) / (k, thread & 7), so that consecutive lanes
+// read consecutive elements (indexing one e^{-2 pi i e / 2048} table by thread * k is a stride-k access: up to 8-way
+// conflicts, which was half of the kernel's shared-memory wavefronts in round 1, profiles/r1_v5_mel_ncu_summary.csv).
 // A CTA is two teams and owns 8 consecutive frames so that the [n_mels, T] output is written in 32-byte runs.
 #pragma once
 
@@ -24,7 +29,9 @@ constexpr int TEAM = 128;                    // threads per FFT
 constexpr int THREADS = 256;                 // two teams per CTA
 constexpr int FRAMES_PER_CTA = 8;
 constexpr int MAX_MELS = 256;
-constexpr int FFT_BUF = NFFT + NFFT / 8 + 8 * (NFFT / 128);      // padded complex elements per transform
+constexpr int FFT_BUF = NFFT + NFFT / 16;    // padded complex elements per transform
+constexpr int TW1_ELEMS = 15 * TEAM;         // pass-1 twiddles e^{-2 pi i t k / 2048}, [k - 1][t]
+constexpr int TW2_ELEMS = 15 * 8;            // pass-2 twiddles e^{-2 pi i n2 k / 128},  [k - 1][n2]
 
 // ---- small in-register DFTs (forward, e^{-2 pi i / n}), natural order in and out
 __host__ __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
@@ -71,31 +78,34 @@ __host__ __device__ __forceinline__ void fft16(float2 (&a)[16]) {
     for (int k = 0; k < 8; ++k) { a[k] = cadd(e[k], o[k]); a[k + 8] = csub(e[k], o[k]); }
 }
 
-// Physical slot of logical element i between the passes: one pad per 8 and eight more per 128 keep the strided
-// accesses of passes 2 and 3 on distinct banks.
-__host__ __device__ __forceinline__ int fft_phys(int i) { return i + (i >> 3) + ((i >> 7) << 3); }
-// Where X[k] lands after pass 3: natural order with one pad per 16 (pass 3 stores with stride 16).
+// Physical slot of logical element i, between the passes and afterwards: one pad per 16 elements. For a half-warp of
+// consecutive threads every access pattern of the three passes then covers 16 distinct 8-byte bank pairs (checked
+// exhaustively by tests/test_host_fft.py).
+__host__ __device__ __forceinline__ int fft_phys(int i) { return i + (i >> 4); }
+// Where X[k] lands after pass 3: the same map (natural order).
 __host__ __device__ __forceinline__ int fft_pos(int k) { return k + (k >> 4); }
-// e^{-2 pi i e / 2048} for 0 <= e < 2048 from the half table tw[k] = e^{-2 pi i k / 2048}, k < 1024.
-__host__ __device__ __forceinline__ float2 fft_tw(const float2* tw, int e) {
-    const float2 w = tw[e & (NFFT / 2 - 1)];
-    return (e & (NFFT / 2)) ? make_float2(-w.x, -w.y) : w;
+// Twiddle tables (built on the host in double precision, copied to shared memory once per CTA):
+//   tw1[(k - 1) * 128 + t]  = e^{-2 pi i t k / 2048}   pass 1, thread t, output k = 1..15
+//   tw2[(k - 1) * 8 + n2]   = e^{-2 pi i n2 k / 128}   pass 2, thread & 7 = n2, output k = 1..15
+__host__ __device__ __forceinline__ float2 fft_twiddle_value(long long num, long long den) {
+    const double a = -2.0 * 3.14159265358979323846 * static_cast<double>(num % den) / static_cast<double>(den);
+    return make_float2(static_cast<float>(cos(a)), static_cast<float>(sin(a)));
 }
 
 // The three passes for thread t of a team; a barrier over the team separates them. `in` holds x[128 n + t], n < 16.
-__host__ __device__ __forceinline__ void fft_pass1(float2* S, const float2* tw, int t, float2 (&a)[16]) {
+__host__ __device__ __forceinline__ void fft_pass1(float2* S, const float2* tw1, int t, float2 (&a)[16]) {
     fft16(a);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) S[fft_phys(k * 128 + t)] = k == 0 ? a[0] : cmul(a[k], fft_tw(tw, t * k));
+    for (int k = 0; k < 16; ++k) S[fft_phys(k * 128 + t)] = k == 0 ? a[0] : cmul(a[k], tw1[(k - 1) * TEAM + t]);
 }
-__host__ __device__ __forceinline__ void fft_pass2(float2* S, const float2* tw, int t) {
+__host__ __device__ __forceinline__ void fft_pass2(float2* S, const float2* tw2, int t) {
     const int s = t >> 3, n2 = t & 7;
     float2 a[16];
 #pragma unroll
     for (int n = 0; n < 16; ++n) a[n] = S[fft_phys(s * 128 + 8 * n + n2)];
     fft16(a);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) S[fft_phys(s * 128 + k * 8 + n2)] = k == 0 ? a[0] : cmul(a[k], fft_tw(tw, 16 * n2 * k));
+    for (int k = 0; k < 16; ++k) S[fft_phys(s * 128 + k * 8 + n2)] = k == 0 ? a[0] : cmul(a[k], tw2[(k - 1) * 8 + n2]);
 }
 // Pass 3 reads two length-8 sub-transforms (u = t, t + 128), and, after a team barrier, writes them in natural order:
 // sub-transform u = k1 * 16 + k2 holds X[k1 + 16 k2 + 256 k3], k3 < 8.
@@ -112,8 +122,8 @@ __host__ __device__ __forceinline__ void fft_pass3_store(float2* S, int t, const
 }
 
 __device__ __forceinline__ float hann_from_tw(const float2* tw, int n) {
-    // periodic Hann: 0.5 - 0.5 cos(2 pi n / N); tw[k].x = cos(2 pi k / N) for k < N/2
-    return n < NFFT / 2 ? 0.5f - 0.5f * tw[n].x : 0.5f + 0.5f * tw[n - NFFT / 2].x;
+    // periodic Hann: 0.5 - 0.5 cos(2 pi n / N); tw[k].x = cos(2 pi k / N) for k < N/2 (global table, read once per CTA)
+    return n < NFFT / 2 ? 0.5f - 0.5f * __ldg(&tw[n]).x : 0.5f + 0.5f * __ldg(&tw[n - NFFT / 2]).x;
 }
 __device__ __forceinline__ void team_sync(int team) { asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(TEAM) : "memory"); }
 
@@ -123,7 +133,7 @@ struct MelArgs {
     long long T;            // frames per clip
     int hop;
     int n_mels;
-    const float2* tw;       // [NFFT/2] exp(-2 pi i k / N)
+    const float2* tw;       // [NFFT/2] exp(-2 pi i k / N) (window), followed by the pass tables: [TW1_ELEMS], [TW2_ELEMS]
     const float* fbT;       // [n_mels, NBINS] band-major filterbank
     const int2* band;       // [n_mels] {first bin, one past last bin}
     float* mel;             // [B, n_mels, T]
@@ -143,7 +153,7 @@ __device__ __forceinline__ float frame_sample(const float* __restrict__ w, long 
 // Transform frames a and b (b may not exist) of one clip by one team: S ends up holding the spectrum of a + i b in
 // natural order (read it through fft_pos). Ends with a team barrier.
 template <bool SPECTRAL>
-__device__ __forceinline__ void fft_frame_pair(float2* S, const float2* tw_s, const float* win_s,
+__device__ __forceinline__ void fft_frame_pair(float2* S, const float2* tw1_s, const float2* tw2_s, const float* win_s,
                                                const float* __restrict__ wave, long long len, long long start_a,
                                                bool has_b, long long start_b, int team, int t) {
     float2 a[16];
@@ -171,9 +181,9 @@ __device__ __forceinline__ void fft_frame_pair(float2* S, const float2* tw_s, co
             a[n] = make_float2(va, vb);
         }
     }
-    fft_pass1(S, tw_s, t, a);
+    fft_pass1(S, tw1_s, t, a);
     team_sync(team);
-    fft_pass2(S, tw_s, t);
+    fft_pass2(S, tw2_s, t);
     team_sync(team);
     float2 ra[8], rb[8];
     fft_pass3_load(S, t, ra, rb);
@@ -195,25 +205,26 @@ constexpr int FB_PACK_CAP = 2304;            // non-zero filterbank weights stag
 __global__ void __launch_bounds__(THREADS, 3)
 mel_power_kernel(MelArgs p, long long groups_per_clip, long long total_groups) {
     extern __shared__ __align__(16) unsigned char fe_smem[];
-    float2* tw_s = reinterpret_cast<float2*>(fe_smem);                               // [NFFT / 2]
-    float2* S_all = tw_s + NFFT / 2;                                                  // [2][FFT_BUF]
+    float2* tw1_s = reinterpret_cast<float2*>(fe_smem);                               // [TW1_ELEMS]
+    float2* tw2_s = tw1_s + TW1_ELEMS;                                                // [TW2_ELEMS]
+    float2* S_all = tw2_s + TW2_ELEMS;                                                // [2][FFT_BUF]
     float* win_s = reinterpret_cast<float*>(S_all + 2 * FFT_BUF);                     // [NFFT]
     float* wpack = win_s + NFFT;                                                      // [FB_PACK_CAP]
     int* woff = reinterpret_cast<int*>(wpack + FB_PACK_CAP);                          // [MAX_MELS + 1]
     float* out_tile = reinterpret_cast<float*>(woff + MAX_MELS + 1);                  // [n_mels][FRAMES_PER_CTA + 1]
     const int team = threadIdx.x / TEAM, t = threadIdx.x % TEAM;
     float2* S = S_all + team * FFT_BUF;
-    // the transform buffer is dead once the bins are split: the two power spectra of the pair live in it afterwards
-    float* pw0 = reinterpret_cast<float*>(S);
-    float* pw1 = pw0 + NBINS + 3;
-    for (int i = threadIdx.x; i < NFFT / 2; i += THREADS) tw_s[i] = p.tw[i];
+    // the transform buffer is dead once the bins are split: the power spectra of the pair live in it afterwards,
+    // interleaved {frame a, frame b} per bin, so that one 8-byte load serves both frames of a filterbank tap
+    float2* pw = S;
+    for (int i = threadIdx.x; i < TW1_ELEMS + TW2_ELEMS; i += THREADS) tw1_s[i] = p.tw[NFFT / 2 + i];
+    for (int i = threadIdx.x; i < NFFT; i += THREADS) win_s[i] = hann_from_tw(p.tw, i);
     if (threadIdx.x == 0) {
         int off = 0;
         for (int m = 0; m < p.n_mels; ++m) { woff[m] = off; const int2 be = p.band[m]; off += max(0, be.y - be.x); }
         woff[p.n_mels] = off;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < NFFT; i += THREADS) win_s[i] = hann_from_tw(tw_s, i);
     const bool packed = woff[p.n_mels] <= FB_PACK_CAP;          // a dense user filterbank falls back to global reads
     if (packed) {
         for (int m = 0; m < p.n_mels; ++m) {
@@ -233,41 +244,54 @@ mel_power_kernel(MelArgs p, long long groups_per_clip, long long total_groups) {
         for (int pr = team * 4; pr < team * 4 + 4; pr += 2) {
             if (pr >= nf) break;                                                      // team-uniform
             const bool has_b = pr + 1 < nf;
-            fft_frame_pair<false>(S, tw_s, win_s, wave, p.S, (f0 + pr) * p.hop, has_b, (f0 + pr + 1) * p.hop, team, t);
-            float pa[9], pb[9];
+            fft_frame_pair<false>(S, tw1_s, tw2_s, win_s, wave, p.S, (f0 + pr) * p.hop, has_b, (f0 + pr + 1) * p.hop, team, t);
+            float2 pab[9];
 #pragma unroll
             for (int q = 0; q < 9; ++q) {
                 const int k = t + q * TEAM;
                 if (k < NBINS) {
                     float2 xa, xb;
                     split_bins(S, k, xa, xb);
-                    pa[q] = (xa.x * xa.x + xa.y * xa.y) * p.inv_wsum;
-                    pb[q] = (xb.x * xb.x + xb.y * xb.y) * p.inv_wsum;
+                    pab[q] = make_float2((xa.x * xa.x + xa.y * xa.y) * p.inv_wsum, (xb.x * xb.x + xb.y * xb.y) * p.inv_wsum);
                 }
             }
             team_sync(team);
 #pragma unroll
             for (int q = 0; q < 9; ++q) {
                 const int k = t + q * TEAM;
-                if (k < NBINS) { pw0[k] = pa[q]; pw1[k] = pb[q]; }
+                if (k < NBINS) pw[k] = pab[q];
             }
             team_sync(team);
-            // banded projection: four lanes per (frame, band), taps interleaved, fixed-order quad reduction
-            for (int o = t >> 2; o < 2 * p.n_mels; o += TEAM / 4) {
-                const int which = o / p.n_mels, m = o - which * p.n_mels;
+            // banded projection: four lanes per band, both frames of the pair per lane, taps interleaved over the
+            // quad, fixed-order quad reduction
+            for (int m = t >> 2; m < p.n_mels; m += TEAM / 4) {
                 const int2 be = p.band[m];
-                const float* pw = which ? pw1 : pw0;
-                float acc = 0.f;
+                float acc0 = 0.f, acc1 = 0.f;
                 if (packed) {
                     const float* wv = wpack + woff[m] - be.x;
-                    for (int k = be.x + quad; k < be.y; k += 4) acc = fmaf(pw[k], wv[k], acc);
+                    for (int k = be.x + quad; k < be.y; k += 4) {
+                        const float2 pv = pw[k];
+                        const float w = wv[k];
+                        acc0 = fmaf(pv.x, w, acc0);
+                        acc1 = fmaf(pv.y, w, acc1);
+                    }
                 } else {
                     const float* fb = p.fbT + static_cast<long long>(m) * NBINS;
-                    for (int k = be.x + quad; k < be.y; k += 4) acc = fmaf(pw[k], __ldg(fb + k), acc);
+                    for (int k = be.x + quad; k < be.y; k += 4) {
+                        const float2 pv = pw[k];
+                        const float w = __ldg(fb + k);
+                        acc0 = fmaf(pv.x, w, acc0);
+                        acc1 = fmaf(pv.y, w, acc1);
+                    }
                 }
-                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-                if (quad == 0) out_tile[m * (FRAMES_PER_CTA + 1) + pr + which] = acc;
+                acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1);
+                acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1);
+                acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2);
+                acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
+                if (quad == 0) {
+                    out_tile[m * (FRAMES_PER_CTA + 1) + pr] = acc0;
+                    out_tile[m * (FRAMES_PER_CTA + 1) + pr + 1] = acc1;       // column pr + 1 <= 8: inside the padded row
+                }
             }
             team_sync(team);
         }
@@ -285,8 +309,8 @@ mel_power_kernel(MelArgs p, long long groups_per_clip, long long total_groups) {
     }
 }
 constexpr size_t mel_smem_bytes(int n_mels) {
-    return sizeof(float2) * (NFFT / 2 + 2 * FFT_BUF) + sizeof(float) * (NFFT + FB_PACK_CAP) + sizeof(int) * (MAX_MELS + 1) +
-           sizeof(float) * n_mels * (FRAMES_PER_CTA + 1);
+    return sizeof(float2) * (TW1_ELEMS + TW2_ELEMS + 2 * FFT_BUF) + sizeof(float) * (NFFT + FB_PACK_CAP) +
+           sizeof(int) * (MAX_MELS + 1) + sizeof(float) * n_mels * (FRAMES_PER_CTA + 1);
 }
 
 struct SpectralArgs {
@@ -295,7 +319,7 @@ struct SpectralArgs {
     long long T;
     int hop;
     float bin_hz;           // sample_rate / NFFT
-    const float2* tw;
+    const float2* tw;       // as MelArgs::tw
     float* out;             // [2, T]
 };
 
@@ -312,24 +336,24 @@ __device__ __forceinline__ float team_sum(float v, float* sh, int team, int t) {
 __global__ void __launch_bounds__(THREADS, 3)
 spectral_stats_kernel(SpectralArgs p) {
     extern __shared__ __align__(16) unsigned char fe_smem[];
-    float2* tw_s = reinterpret_cast<float2*>(fe_smem);                               // [NFFT / 2]
-    float2* S_all = tw_s + NFFT / 2;                                                  // [2][FFT_BUF]
+    float2* tw1_s = reinterpret_cast<float2*>(fe_smem);                               // [TW1_ELEMS]
+    float2* tw2_s = tw1_s + TW1_ELEMS;                                                // [TW2_ELEMS]
+    float2* S_all = tw2_s + TW2_ELEMS;                                                // [2][FFT_BUF]
     float* win_s = reinterpret_cast<float*>(S_all + 2 * FFT_BUF);                     // [NFFT]
     __shared__ float red[8];
     const int team = threadIdx.x / TEAM, t = threadIdx.x % TEAM;
     float2* S = S_all + team * FFT_BUF;
     float* mag0 = reinterpret_cast<float*>(S);         // the transform buffer is dead once the bins are split
     float* mag1 = mag0 + NBINS + 3;
-    for (int i = threadIdx.x; i < NFFT / 2; i += THREADS) tw_s[i] = p.tw[i];
-    __syncthreads();
-    for (int i = threadIdx.x; i < NFFT; i += THREADS) win_s[i] = hann_from_tw(tw_s, i);
+    for (int i = threadIdx.x; i < TW1_ELEMS + TW2_ELEMS; i += THREADS) tw1_s[i] = p.tw[NFFT / 2 + i];
+    for (int i = threadIdx.x; i < NFFT; i += THREADS) win_s[i] = hann_from_tw(p.tw, i);
     __syncthreads();
     const long long pairs = (p.T + 1) / 2;
     // one frame pair per team and iteration
     for (long long pr = static_cast<long long>(blockIdx.x) * 2 + team; pr < pairs; pr += static_cast<long long>(gridDim.x) * 2) {
         const long long fa = 2 * pr, fb = fa + 1;
         const bool has_b = fb < p.T;
-        fft_frame_pair<true>(S, tw_s, win_s, p.wave, p.S, fa * p.hop, has_b, fb * p.hop, team, t);
+        fft_frame_pair<true>(S, tw1_s, tw2_s, win_s, p.wave, p.S, fa * p.hop, has_b, fb * p.hop, team, t);
         float ma[9], mb[9];
 #pragma unroll
         for (int q = 0; q < 9; ++q) {
@@ -374,7 +398,7 @@ spectral_stats_kernel(SpectralArgs p) {
         team_sync(team);
     }
 }
-constexpr size_t spectral_smem_bytes() { return sizeof(float2) * (NFFT / 2 + 2 * FFT_BUF) + sizeof(float) * NFFT; }
+constexpr size_t spectral_smem_bytes() { return sizeof(float2) * (TW1_ELEMS + TW2_ELEMS + 2 * FFT_BUF) + sizeof(float) * NFFT; }
 
 // dense [NBINS, n_mels] filterbank -> band-major copy + per-band non-zero range (one CTA per band)
 __global__ void __launch_bounds__(128)

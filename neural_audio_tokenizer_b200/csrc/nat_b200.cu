@@ -133,6 +133,7 @@ struct Workspace {
 };
 
 constexpr size_t kWsFixed = 4096;
+constexpr int kMaxStacks = 2;             // S0-S3 and A0-A3 of one tokenizer per call
 
 size_t ws_per_row(int dp, int L) { return static_cast<size_t>(dp) * 6 + 16 + 4 + sizeof(nat::gemm::Cand) + 8 * L + 4; }
 
@@ -171,31 +172,35 @@ static cudaError_t stack_kernel_attrs() {
 }
 
 // One persistent launch of the fused stack kernel: plain grid (pair == 1) or clusters of two CTAs (pair == 2).
-struct StackMaps { CUtensorMap a0, a1, aw0, aw1, b0, b1; };
+struct StackMaps { CUtensorMap a0, aw, b; };
 
 template <int NV>
 static cudaError_t launch_stack(int pair, int grid, cudaStream_t st, const StackMaps& m,
-                                const nat::stack::StackArgs& sa) {
+                                const nat::stack::StackArgs& sa, bool programmatic) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = dim3(grid, 1, 1);
     cfg.blockDim = dim3(nat::stack::NUM_THREADS, 1, 1);
     cfg.dynamicSmemBytes = nat::stack::SMEM_BYTES;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = pair;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    // a stack that shares nothing written by the launch before it (the other stack of the same tokenizer) may start
+    // on every SM that launch has already left: programmatic dependent launch, no wait inside the kernel
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = programmatic ? 2 : 1;
     // the instrumented instantiation runs only while counters or timing experiments are switched on
     const bool dbg = sa.dbg != nullptr || sa.dbg_mode != 0;
     if (pair == 2)
-        return dbg ? cudaLaunchKernelEx(&cfg, nat::stack::rvq_stack_kernel<NV, 2, true>, m.a0, m.a1, m.aw0, m.aw1, m.b0, m.b1, sa)
-                   : cudaLaunchKernelEx(&cfg, nat::stack::rvq_stack_kernel<NV, 2, false>, m.a0, m.a1, m.aw0, m.aw1, m.b0, m.b1, sa);
-    return dbg ? cudaLaunchKernelEx(&cfg, nat::stack::rvq_stack_kernel<NV, 1, true>, m.a0, m.a1, m.aw0, m.aw1, m.b0, m.b1, sa)
-               : cudaLaunchKernelEx(&cfg, nat::stack::rvq_stack_kernel<NV, 1, false>, m.a0, m.a1, m.aw0, m.aw1, m.b0, m.b1, sa);
+        return dbg ? cudaLaunchKernelEx(&cfg, nat::stack::rvq_stack_kernel<NV, 2, true>, m.a0, m.aw, m.b, sa)
+                   : cudaLaunchKernelEx(&cfg, nat::stack::rvq_stack_kernel<NV, 2, false>, m.a0, m.aw, m.b, sa);
+    return dbg ? cudaLaunchKernelEx(&cfg, nat::stack::rvq_stack_kernel<NV, 1, true>, m.a0, m.aw, m.b, sa)
+               : cudaLaunchKernelEx(&cfg, nat::stack::rvq_stack_kernel<NV, 1, false>, m.a0, m.aw, m.b, sa);
 }
 
 // Caller-owned state of the host-buffer entry points: a two-slot device staging arena (grown on demand), the copy
@@ -426,87 +431,72 @@ static bool fused_pair() {
     const char* e = getenv("NAT_RVQ_PAIR");
     return e == nullptr || atoi(e) != 1;
 }
+static bool pdl_enabled() {
+    const char* e = getenv("NAT_RVQ_PDL");              // read every call: the probes flip it for A/B measurements
+    return (e == nullptr || atoi(e) != 0) && g_prof == nullptr;   // timed per launch: every kernel alone
+}
 static int fused_group(int pair) {
     const char* e = getenv("NAT_RVQ_GROUP");
     const int v = e ? atoi(e) : 0;
     return v >= 1 ? v : (pair == 2 ? 3 : 2);      // measured on B200: 270k x 768, K = 1024 (profiles/)
 }
 
-// One launch of the fused stack kernel over up to two stacks (same K / D) on the same frame range.
+// One launch of the fused stack kernel: one stack over one range of frames.
 struct StackLaunch {
-    const nat_rvq_codebooks* cb[nat::stack::MAX_STACKS] = {nullptr, nullptr};
-    int n_stacks = 1;
-    const float* r0[2] = {nullptr, nullptr};
-    const float4* rowinfo0[2] = {nullptr, nullptr};
-    const float* rowamax0[2] = {nullptr, nullptr};
-    float* r_work[2] = {nullptr, nullptr}; __half* a_work[2] = {nullptr, nullptr};
-    float4* rowinfo_work[2] = {nullptr, nullptr}; float* rowamax_work[2] = {nullptr, nullptr};
-    void* codes[2] = {nullptr, nullptr}; long long codes_ld[2] = {0, 0}, code_off[2] = {0, 0};
-    double* row_loss[2] = {nullptr, nullptr}; long long loss_ld = 0;
-    unsigned long long* stats[2] = {nullptr, nullptr};
-    StackMaps maps;              // a0 / a1 / aw0 / aw1 filled by the caller; b0 / b1 come from the handles
+    const nat_rvq_codebooks* cb = nullptr;
+    const float* r0 = nullptr; const float4* rowinfo0 = nullptr; const float* rowamax0 = nullptr;   // prepared rows (layer 0)
+    float* r = nullptr; __half* a = nullptr; float4* rowinfo = nullptr; float* rowamax = nullptr;      // rows the kernel writes
+    void* codes = nullptr; long long codes_ld = 0, code_off = 0;
+    double* row_loss = nullptr; long long loss_ld = 0;
+    unsigned long long* stats = nullptr;
+    CUtensorMap map_a0, map_a;   // operand rows: prepared / written by the kernel (may be the same buffer)
     int n_rows = 0, code_dtype = NAT_CODES_I16;
+    bool programmatic = false;   // may overlap the tail of the launch before it (shares nothing that launch writes)
 };
 
-static int launch_fused_stacks(StackLaunch& sl, cudaStream_t st) {
+static int launch_fused_stack(const StackLaunch& sl, cudaStream_t st) {
     using namespace nat;
-    const nat_rvq_codebooks* cb = sl.cb[0];
+    const nat_rvq_codebooks* cb = sl.cb;
     const int n_tiles = (sl.n_rows + stack::BLOCK_M - 1) / stack::BLOCK_M;
     stack::StackArgs sa;
     memset(&sa, 0, sizeof sa);
-    sa.n_stacks = sl.n_stacks;
-    for (int i = 0; i < sl.n_stacks; ++i) {
-        const nat_rvq_codebooks* c = sl.cb[i];
-        stack::StackRef& r = sa.s[i];
-        r.cbf = c->cbf; r.cn64 = c->cn64; r.cn32 = c->cn32; r.lc = c->lc;
-        r.r0 = sl.r0[i]; r.rowinfo0 = sl.rowinfo0[i]; r.rowamax0 = sl.rowamax0[i];
-        r.r_work = sl.r_work[i]; r.a_work = sl.a_work[i]; r.rowinfo_work = sl.rowinfo_work[i]; r.rowamax_work = sl.rowamax_work[i];
-        r.codes = sl.codes[i]; r.codes_ld = sl.codes_ld[i]; r.code_off = sl.code_off[i];
-        r.row_loss = sl.row_loss[i]; r.loss_ld = sl.loss_ld;
-        r.stats = sl.stats[i];
-        r.L = c->L;
-        // Residual write-back policy of the hot update form: the residual entering the last layer is never needed in
-        // memory (only its fp16 operand is); which of the other layers write it back is a measured choice (a layer
-        // whose bit is clear leaves later layers to replay its update from the emitted code: one extra L2 gather).
-        r.store_mask = 0x55555555 & ((1 << std::max(0, c->L - 2)) - 1);
-        { const char* e = getenv("NAT_RVQ_STORE_MASK"); if (e) r.store_mask &= atoi(e); }
-        { const char* e = getenv("NAT_RVQ_STORE_MASK_SET"); if (e) r.store_mask = atoi(e); }      // A/B measurements
-    }
+    stack::StackRef& r = sa.s;
+    r.cbf = cb->cbf; r.cn64 = cb->cn64; r.cn32 = cb->cn32; r.lc = cb->lc;
+    r.r0 = sl.r0; r.rowinfo0 = sl.rowinfo0; r.rowamax0 = sl.rowamax0;
+    r.r = sl.r; r.a = sl.a; r.rowinfo = sl.rowinfo; r.rowamax = sl.rowamax;
+    r.codes = sl.codes; r.codes_ld = sl.codes_ld; r.code_off = sl.code_off;
+    r.row_loss = sl.row_loss; r.loss_ld = sl.loss_ld;
+    r.stats = sl.stats;
+    r.L = cb->L;
+    // Residual write-back policy of the hot update form: the residual entering the last layer is never needed in
+    // memory (only its fp16 operand is), and writing back after every other layer only (later layers replay the
+    // skipped update from the emitted code, one extra L2 gather) measured faster than every layer or none.
+    r.store_mask = 0x55555555 & ((1 << std::max(0, cb->L - 2)) - 1);
+    { const char* e = getenv("NAT_RVQ_STORE_MASK"); if (e) r.store_mask &= atoi(e); }
+    { const char* e = getenv("NAT_RVQ_STORE_MASK_SET"); if (e) r.store_mask = atoi(e); }      // A/B measurements
     sa.n_rows = sl.n_rows; sa.n_tiles = n_tiles; sa.K = cb->K; sa.kp = cb->kp; sa.dp = cb->dp;
     sa.code_dtype = sl.code_dtype;
-    bool dbg_on = false;
-    for (int i = 0; i < sl.n_stacks; ++i) dbg_on = dbg_on || sl.cb[i]->stack_dbg_on;
-    sa.dbg = dbg_on ? cb->stack_dbg : nullptr;
+    sa.dbg = cb->stack_dbg_on ? cb->stack_dbg : nullptr;
     { const char* e = getenv("NAT_RVQ_DBG_MODE"); sa.dbg_mode = e ? atoi(e) : 0; }
     // CTA pairs (one tcgen05.mma.cta_group::2 per two SMs) once there is more than one tile; NAT_RVQ_PAIR=1 keeps
     // the single-CTA form for A/B measurements.
     const int pair = (n_tiles >= 2 && cb->sm_count >= 2 && cb->pair_ok && fused_pair()) ? 2 : 1;
-    // one stack: as many CTAs as tiles, up to one per SM. Two stacks: the SMs are split between them (whole CTA
-    // pairs), each half at most as many CTAs as there are tiles.
-    int grid, split;
-    if (sl.n_stacks == 1) {
-        grid = pair == 2 ? std::min((n_tiles + 1) & ~1, cb->sm_count & ~1) : std::min(n_tiles, cb->sm_count);
-        split = grid;
-    } else {
-        const int half = pair == 2 ? std::min((n_tiles + 1) & ~1, (cb->sm_count / 2) & ~1) : std::min(n_tiles, cb->sm_count / 2);
-        split = half;
-        grid = 2 * half;
-    }
-    sa.split = split;
-    sl.maps.b0 = pair == 2 ? sl.cb[0]->map_b_half : sl.cb[0]->map_b;
-    const nat_rvq_codebooks* cb1 = sl.cb[sl.n_stacks > 1 ? 1 : 0];
-    sl.maps.b1 = pair == 2 ? cb1->map_b_half : cb1->map_b;
+    const int grid = pair == 2 ? std::min((n_tiles + 1) & ~1, cb->sm_count & ~1) : std::min(n_tiles, cb->sm_count);
+    StackMaps maps;
+    maps.a0 = sl.map_a0; maps.aw = sl.map_a;
+    maps.b = pair == 2 ? cb->map_b_half : cb->map_b;
     sa.group = fused_group(pair);
     const int nv = (cb->dp / 4 + 31) / 32;
+    const bool pdl = sl.programmatic && pdl_enabled();
     cudaError_t le = cudaSuccess;
     NAT_LAUNCH(1, st, {
 #ifdef NAT_ONLY_NV                                   /* A/B builds: one instantiation, a quarter of the compile time */
-        le = launch_stack<NAT_ONLY_NV>(pair, grid, st, sl.maps, sa);
+        le = launch_stack<NAT_ONLY_NV>(pair, grid, st, maps, sa, pdl);
 #else
-        if (nv <= 2) le = launch_stack<2>(pair, grid, st, sl.maps, sa);
-        else if (nv <= 4) le = launch_stack<4>(pair, grid, st, sl.maps, sa);
-        else if (nv <= 6) le = launch_stack<6>(pair, grid, st, sl.maps, sa);
-        else le = launch_stack<8>(pair, grid, st, sl.maps, sa);
+        if (nv <= 2) le = launch_stack<2>(pair, grid, st, maps, sa, pdl);
+        else if (nv <= 4) le = launch_stack<4>(pair, grid, st, maps, sa, pdl);
+        else if (nv <= 6) le = launch_stack<6>(pair, grid, st, maps, sa, pdl);
+        else le = launch_stack<8>(pair, grid, st, maps, sa, pdl);
 #endif
     });
     NAT_CUDA(le);
@@ -537,17 +527,17 @@ static int encode_chunk(const EncodeCall& c, const Workspace& ws, const CUtensor
     const bool fused = !c.exact && c.temperatures == nullptr && fused_enabled() && cb->dp <= 1024 && c.scores == nullptr;
     if (!fused) NAT_CUDA(cudaMemsetAsync(ws.scan_count, 0, sizeof(int) * cb->L, st));   // only the per-layer kernels list scans
     if (fused) {
-        // one persistent launch for all L layers (rvq_stack_sm100.cuh); one stack: the update warps write in place
+        // one persistent launch for all L layers (rvq_stack_sm100.cuh); the update warps write in place
         StackLaunch sl;
-        sl.cb[0] = cb; sl.n_stacks = 1;
-        sl.r0[0] = ws.r; sl.rowinfo0[0] = ws.rowinfo; sl.rowamax0[0] = ws.rowamax;
-        sl.r_work[0] = ws.r; sl.a_work[0] = ws.a; sl.rowinfo_work[0] = ws.rowinfo; sl.rowamax_work[0] = ws.rowamax;
-        sl.codes[0] = c.codes; sl.codes_ld[0] = c.N; sl.code_off[0] = n0;
-        sl.row_loss[0] = c.want_loss ? ws.row_loss : nullptr; sl.loss_ld = ws.rows;
-        sl.stats[0] = c.stats;
-        sl.maps.a0 = map_a; sl.maps.a1 = map_a; sl.maps.aw0 = map_a; sl.maps.aw1 = map_a;
+        sl.cb = cb;
+        sl.r0 = ws.r; sl.rowinfo0 = ws.rowinfo; sl.rowamax0 = ws.rowamax;
+        sl.r = ws.r; sl.a = ws.a; sl.rowinfo = ws.rowinfo; sl.rowamax = ws.rowamax;
+        sl.codes = c.codes; sl.codes_ld = c.N; sl.code_off = n0;
+        sl.row_loss = c.want_loss ? ws.row_loss : nullptr; sl.loss_ld = ws.rows;
+        sl.stats = c.stats;
+        sl.map_a0 = map_a; sl.map_a = map_a;
         sl.n_rows = n; sl.code_dtype = c.code_dtype;
-        if (int rc = launch_fused_stacks(sl, st)) return rc;
+        if (int rc = launch_fused_stack(sl, st)) return rc;
         if (c.want_loss)
             for (int l = 0; l < cb->L; ++l)
                 NAT_LAUNCH(4, st, rows::reduce_loss_kernel<<<1, 1024, 0, st>>>(ws.row_loss + static_cast<long long>(l) * ws.rows,
@@ -928,9 +918,9 @@ int nat_debug_rvq_scores(const nat_rvq_codebooks* cb, int layer, const float* ro
 
 // ------------------------------------------------------------------------------------------------- several stacks
 // The stacks of one tokenizer (S0-S3, A0-A3) in one call. Stacks that quantise the same frames (equal x pointers)
-// share one layer-0 preparation; all of them share ONE persistent launch of the fused kernel per chunk of frames
-// (stack 1's layers follow stack 0's for every group of tiles). Shapes the fused form does not cover (different K or
-// D, D > 1024, inputs of a few tiles, NAT_RVQ_FUSED=0) run stack after stack through nat_rvq_encode_f32.
+// share one layer-0 preparation, and the second stack's persistent launch is a programmatic dependent launch that
+// fills the SMs the first one has already left. Shapes the fused kernel does not cover (different K or D, D > 1024,
+// inputs of a few tiles, NAT_RVQ_FUSED=0) run stack after stack through nat_rvq_encode_f32.
 namespace {
 
 bool stacks_fusable(const nat_rvq_codebooks* const* stacks, int n_stacks, long long N) {
@@ -1035,12 +1025,12 @@ int nat_rvq_encode_stacks_f32(const nat_rvq_codebooks* const* stacks, int n_stac
     if (!carve_multi(workspace_dev, workspace_bytes, s0->dp, n_inputs, std::min<long long>(N, chunk_cap_rows()), &ws))
         return fail(NAT_ERR_WORKSPACE, "workspace of %zu bytes cannot hold one 128-frame tile (need %zu)", workspace_bytes,
                     multi_ws_bytes(s0->dp, n_inputs, 128));
-    StackMaps maps;
-    if (int rc = make_map_f16(&maps.a0, ws.a_prep[0], ws.rows, s0->dp, 128)) return rc;
-    if (n_inputs == 2) { if (int rc = make_map_f16(&maps.a1, ws.a_prep[1], ws.rows, s0->dp, 128)) return rc; }
-    else maps.a1 = maps.a0;
-    if (int rc = make_map_f16(&maps.aw0, ws.a_work[0], ws.rows, s0->dp, 128)) return rc;
-    if (int rc = make_map_f16(&maps.aw1, ws.a_work[1], ws.rows, s0->dp, 128)) return rc;
+    CUtensorMap map_prep[2], map_work[2];
+    if (int rc = make_map_f16(&map_prep[0], ws.a_prep[0], ws.rows, s0->dp, 128)) return rc;
+    if (n_inputs == 2) { if (int rc = make_map_f16(&map_prep[1], ws.a_prep[1], ws.rows, s0->dp, 128)) return rc; }
+    else map_prep[1] = map_prep[0];
+    for (int i = 0; i < 2; ++i)
+        if (int rc = make_map_f16(&map_work[i], ws.a_work[i], ws.rows, s0->dp, 128)) return rc;
     if (s0->dp != s0->D) {          // padded columns of the operand rows are never written by the row kernels
         for (int i = 0; i < n_inputs; ++i) NAT_CUDA(cudaMemsetAsync(ws.a_prep[i], 0, static_cast<size_t>(ws.rows) * s0->dp * 2, st));
         for (int i = 0; i < 2; ++i) NAT_CUDA(cudaMemsetAsync(ws.a_work[i], 0, static_cast<size_t>(ws.rows) * s0->dp * 2, st));
@@ -1058,19 +1048,18 @@ int nat_rvq_encode_stacks_f32(const nat_rvq_codebooks* const* stacks, int n_stac
             w1.r = ws.r_prep[1]; w1.a = ws.a_prep[1]; w1.rowinfo = ws.rowinfo[1]; w1.rowamax = ws.rowamax[1];
             if (int rc = launch_layer0_prep(s1, w1, x_dev[1], layout, T, n0, n, st)) return rc;
         }
-        StackLaunch sl;
-        sl.n_stacks = 2;
         for (int i = 0; i < 2; ++i) {
-            sl.cb[i] = stacks[i];
-            sl.r0[i] = ws.r_prep[i]; sl.rowinfo0[i] = ws.rowinfo[i]; sl.rowamax0[i] = ws.rowamax[i];
-            sl.codes[i] = static_cast<char*>(codes_out_dev) + (i == 0 ? 0 : static_cast<long long>(s0->L) * N * cbytes);
-            sl.codes_ld[i] = N; sl.code_off[i] = n0;
-            sl.r_work[i] = ws.r_work[i]; sl.a_work[i] = ws.a_work[i];
-            sl.rowinfo_work[i] = ws.rowinfo_work[i]; sl.rowamax_work[i] = ws.rowamax_work[i];
+            StackLaunch sl;
+            sl.cb = stacks[i];
+            sl.r0 = ws.r_prep[i]; sl.rowinfo0 = ws.rowinfo[i]; sl.rowamax0 = ws.rowamax[i];
+            sl.r = ws.r_work[i]; sl.a = ws.a_work[i]; sl.rowinfo = ws.rowinfo_work[i]; sl.rowamax = ws.rowamax_work[i];
+            sl.codes = static_cast<char*>(codes_out_dev) + (i == 0 ? 0 : static_cast<long long>(s0->L) * N * cbytes);
+            sl.codes_ld = N; sl.code_off = n0;
+            sl.map_a0 = map_prep[i]; sl.map_a = map_work[i];
+            sl.n_rows = n; sl.code_dtype = code_dtype;
+            sl.programmatic = i == 1;       // shares only the prepared rows with stack 0's launch, which never writes them
+            if (int rc = launch_fused_stack(sl, st)) return rc;
         }
-        sl.maps = maps;
-        sl.n_rows = n; sl.code_dtype = code_dtype;
-        if (int rc = launch_fused_stacks(sl, st)) return rc;
     }
     return NAT_OK;
 }
@@ -1119,7 +1108,7 @@ int nat_host_ctx_destroy(nat_host_ctx* ctx) {
 // stacks come back as one [sum L, N] host array.
 int nat_tokenize_host_f32(nat_host_ctx* ctx, const nat_rvq_codebooks* const* stacks, int n_stacks, const float* x_host,
                           int layout, int64_t B, int64_t T, void* codes_out_host, int code_dtype, void* stream) {
-    if (ctx == nullptr || stacks == nullptr || n_stacks < 1 || n_stacks > nat::stack::MAX_STACKS || x_host == nullptr ||
+    if (ctx == nullptr || stacks == nullptr || n_stacks < 1 || n_stacks > kMaxStacks || x_host == nullptr ||
         codes_out_host == nullptr)
         return fail(NAT_ERR_INVALID_ARGUMENT, "null argument or unsupported stack count");
     if (code_dtype < NAT_CODES_I64 || code_dtype > NAT_CODES_I16) return fail(NAT_ERR_INVALID_ARGUMENT, "bad code dtype");
@@ -1158,7 +1147,7 @@ int nat_tokenize_host_f32(nat_host_ctx* ctx, const nat_rvq_codebooks* const* sta
     for (int s = 0; s < 2; ++s) { xs[s] = reinterpret_cast<float*>(base); base += round_up(x_slot, 256);
                                   cs[s] = base; base += round_up(c_slot, 256); }
     void* wsp = base;
-    const float* xin[nat::stack::MAX_STACKS];
+    const float* xin[kMaxStacks];
     // copy stream: H2D(i) ; compute stream waits ev[s], encodes, D2H codes; copy stream waits ev[2+s] before reuse.
     NAT_CUDA(cudaEventRecord(ctx->ev[2], st)); NAT_CUDA(cudaEventRecord(ctx->ev[3], st));
     int slot = 0;
@@ -1234,13 +1223,17 @@ int get_plan(int sample_rate, int n_mels, FePlan** out) {
     FePlan plan;
     NAT_CUDA(cudaDeviceGetAttribute(&plan.sm_count, cudaDevAttrMultiProcessorCount, dev));
     const int N = nat::fe::NFFT, NB = nat::fe::NBINS;
-    std::vector<float2> tw(N / 2);
-    for (int k = 0; k < N / 2; ++k) {
-        const double a = -2.0 * M_PI * k / N;
-        tw[k] = make_float2(static_cast<float>(std::cos(a)), static_cast<float>(std::sin(a)));
+    // [N/2] e^{-2 pi i k / N} (the window), then the per-pass twiddle tables in the order the threads read them
+    std::vector<float2> tw(N / 2 + nat::fe::TW1_ELEMS + nat::fe::TW2_ELEMS);
+    for (int k = 0; k < N / 2; ++k) tw[k] = nat::fe::fft_twiddle_value(k, N);
+    for (int k = 1; k < 16; ++k) {
+        for (int t = 0; t < nat::fe::TEAM; ++t)
+            tw[N / 2 + (k - 1) * nat::fe::TEAM + t] = nat::fe::fft_twiddle_value(static_cast<long long>(t) * k, N);
+        for (int n2 = 0; n2 < 8; ++n2)
+            tw[N / 2 + nat::fe::TW1_ELEMS + (k - 1) * 8 + n2] = nat::fe::fft_twiddle_value(static_cast<long long>(n2) * k, 128);
     }
-    NAT_CUDA(cudaMalloc(&plan.tw, sizeof(float2) * N / 2));
-    NAT_CUDA(cudaMemcpy(plan.tw, tw.data(), sizeof(float2) * N / 2, cudaMemcpyHostToDevice));
+    NAT_CUDA(cudaMalloc(&plan.tw, sizeof(float2) * tw.size()));
+    NAT_CUDA(cudaMemcpy(plan.tw, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice));
     if (n_mels > 0) {
         // HTK triangles exactly as torchaudio.functional.melscale_fbanks(norm=None) defines them (f_min 0, f_max sr//2)
         std::vector<float> fbT(static_cast<size_t>(n_mels) * NB, 0.f);
@@ -1279,8 +1272,44 @@ int64_t nat_spectral_num_frames(int64_t S, int n_fft, int hop) {
     return S >= n_fft ? 1 + (S - n_fft) / hop : 1;
 }
 
+// Banded form of a dense [n_fft/2+1, n_mels] filterbank: [n_mels, NBINS] band-major weights, then {first, one past
+// last} non-zero bin per band. Prepared once per transform object and handed to nat_mel_power_banded_f32.
+static size_t banded_weights_bytes(int n_mels) { return static_cast<size_t>(round_up(static_cast<long long>(n_mels) * nat::fe::NBINS * 4, 256)); }
+
+size_t nat_mel_filterbank_bytes(int n_mels) {
+    return n_mels > 0 ? banded_weights_bytes(n_mels) + sizeof(int2) * static_cast<size_t>(n_mels) : 0;
+}
+
+int nat_mel_filterbank_prepare(const float* fb_dev, int n_mels, void* banded_out_dev, void* stream) {
+    using namespace nat;
+    if (fb_dev == nullptr || banded_out_dev == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null device pointer");
+    if (n_mels < 1 || n_mels > fe::MAX_MELS) return fail(NAT_ERR_UNSUPPORTED, "unsupported n_mels %d", n_mels);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* base = static_cast<char*>(banded_out_dev);
+    NAT_LAUNCH(7, st, fe::fb_to_banded_kernel<<<n_mels, 128, 0, st>>>(fb_dev, n_mels, reinterpret_cast<float*>(base),
+                                                                   reinterpret_cast<int2*>(base + banded_weights_bytes(n_mels))));
+    NAT_CUDA(cudaGetLastError());
+    return NAT_OK;
+}
+
+static int mel_power_impl(const float* wave_dev, int64_t B, int64_t S, int sample_rate, int n_fft, int hop, int n_mels,
+                          const float* fb_dev, const void* fb_banded_dev, float* mel_out_dev, float* logmel_out_dev,
+                          void* stream);
+
 int nat_mel_power_f32(const float* wave_dev, int64_t B, int64_t S, int sample_rate, int n_fft, int hop, int n_mels,
                       const float* fb_dev, float* mel_out_dev, float* logmel_out_dev, void* stream) {
+    return mel_power_impl(wave_dev, B, S, sample_rate, n_fft, hop, n_mels, fb_dev, nullptr, mel_out_dev, logmel_out_dev, stream);
+}
+
+int nat_mel_power_banded_f32(const float* wave_dev, int64_t B, int64_t S, int sample_rate, int n_fft, int hop, int n_mels,
+                             const void* fb_banded_dev, float* mel_out_dev, float* logmel_out_dev, void* stream) {
+    if (fb_banded_dev == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null banded filterbank");
+    return mel_power_impl(wave_dev, B, S, sample_rate, n_fft, hop, n_mels, nullptr, fb_banded_dev, mel_out_dev, logmel_out_dev, stream);
+}
+
+static int mel_power_impl(const float* wave_dev, int64_t B, int64_t S, int sample_rate, int n_fft, int hop, int n_mels,
+                          const float* fb_dev, const void* fb_banded_dev, float* mel_out_dev, float* logmel_out_dev,
+                          void* stream) {
     using namespace nat;
     if (wave_dev == nullptr || mel_out_dev == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null device pointer");
     if (n_fft != fe::NFFT) return fail(NAT_ERR_UNSUPPORTED, "n_fft must be 2048 (the reference hard-codes it), got %d", n_fft);
@@ -1298,8 +1327,12 @@ int nat_mel_power_f32(const float* wave_dev, int64_t B, int64_t S, int sample_ra
     // A caller-supplied filterbank is converted to the banded form into scratch that belongs to THIS call
     // (stream-ordered allocation): concurrent calls on different streams never share it.
     char* fb_scratch = nullptr;
-    if (fb_dev != nullptr) {
-        const size_t fbt_bytes = static_cast<size_t>(round_up(static_cast<long long>(n_mels) * fe::NBINS * 4, 256));
+    if (fb_banded_dev != nullptr) {
+        const char* base = static_cast<const char*>(fb_banded_dev);
+        p.fbT = reinterpret_cast<const float*>(base);
+        p.band = reinterpret_cast<const int2*>(base + banded_weights_bytes(n_mels));
+    } else if (fb_dev != nullptr) {
+        const size_t fbt_bytes = banded_weights_bytes(n_mels);
         NAT_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&fb_scratch), fbt_bytes + sizeof(int2) * n_mels, st));
         float* fbT_user = reinterpret_cast<float*>(fb_scratch);
         int2* band_user = reinterpret_cast<int2*>(fb_scratch + fbt_bytes);

@@ -12,6 +12,15 @@
 // The live residual / operand rows of all CTAs together exceed L2, so they travel through HBM between layers; the
 // write-back policy (`store_mask`) keeps that traffic to one residual write per four-layer stack.
 //
+// Two stacks of one tokenizer (S0-S3, A0-A3) that quantise the same frames share ONE layer-0 preparation: layer 0 of a
+// tile reads the prepared rows (r0 / its fp16 operand / rowinfo0), which this kernel never writes when the rows it
+// writes (r / a / rowinfo / rowamax) are separate buffers, and the second stack's launch is a programmatic dependent
+// launch: every CTA releases its dependents at once (the stacks share nothing this kernel writes), so the second
+// stack's CTAs take over the SMs one by one as the first stack's CTAs run out of tiles, instead of waiting for its
+// slowest CTA. (Both stacks in one launch -- the grid split between them, or (stack, tile) units dealt over the whole
+// grid -- was built and measured in round 2: no faster than two launches, and the per-stack indirection cost 3-7 %
+// in the update warps; profiles/r2_*.log, DESIGN.md.)
+//
 // Warp roles (768 threads, launched as clusters of two CTAs: see the kernel's comment):
 //   warps 0..3    candidates: tcgen05.ld of the accumulators, coarse score, running-threshold candidate list
 //   warps 4..19   update: exact decision (fp64 re-rank where the window demands it), residual update in the
@@ -32,30 +41,6 @@
 
 #ifndef NAT_UPD_WARPS
 #define NAT_UPD_WARPS 16
-#endif
-// A/B knobs of the update / candidate roles (measured on B200, profiles/): every one of them trades registers for
-// overlap, and this kernel pays for every spilled register twice (issue slots and L1 wavefronts next to the MMA's
-// operand reads), so each is decided by measurement, not by taste.
-#ifndef NAT_FORCE_SI0
-#define NAT_FORCE_SI0 0          // 1: single-stack build (the stack index is a compile-time constant)
-#endif
-#ifndef NAT_RI_SMEM
-#define NAT_RI_SMEM 1            // 1: {alpha, window, max |r|} of a group's tiles travel between layers in shared memory
-#endif
-#ifndef NAT_UPD_PIPELINE
-#define NAT_UPD_PIPELINE 0       // 0: load row, load code, update, store. 1: the next row's loads reuse each register
-#endif                           //    group as soon as it is free. 2: the next row's loads follow this row's stores
-#ifndef NAT_UPD_PRELOAD
-#define NAT_UPD_PRELOAD 0        // 1: the first row's residual is requested before the wait for the candidates
-#endif
-#ifndef NAT_UPD_JREP
-#define NAT_UPD_JREP 0           // 1: codes needed by replays are fetched at the start of the job into registers
-#endif
-#ifndef NAT_UPD_PAIR_RERANK
-#define NAT_UPD_PAIR_RERANK 0    // 1: the exact re-rank scores two candidates per step
-#endif
-#ifndef NAT_SCAN_RECOMPUTE
-#define NAT_SCAN_RECOMPUTE 0     // 1: the scores of a listed eight-group are formed again instead of kept alive (fewer registers)
 #endif
 #ifndef NAT_REGS_EPI
 #define NAT_REGS_EPI 88
@@ -96,7 +81,6 @@ constexpr int LCAP = 16;         // eight-code groups listed per frame (compacte
 constexpr int HCAP = 15;         // candidates handed to the update warps per frame (one 32-byte record: count + 15 indices)
 constexpr int HAND_BYTES = 32;
 constexpr unsigned HAND_SCAN = 0xFFFFu;
-constexpr int RI_SLOTS = 4;      // tiles of a group whose per-frame {alpha, window, max |r|} travel between layers in shared memory
 
 #ifndef NAT_STAGES_PAIR
 #define NAT_STAGES_PAIR 6
@@ -112,38 +96,26 @@ struct Smem {
     static constexpr int OFF_LIST_I = OFF_LIST_S + LCAP * BLOCK_M * 4;
     static constexpr int OFF_HAND = OFF_LIST_I + LCAP * BLOCK_M * 4;
     static constexpr int OFF_CN = OFF_HAND + 2 * BLOCK_M * HAND_BYTES;    // [2][BLOCK_N] ||c||^2 of the chunk being scored / the next
-    static constexpr int OFF_RI = OFF_CN + 2 * BLOCK_N * 4;                // [RI_SLOTS][BLOCK_M] {alpha, window} of the next layer
-    static constexpr int OFF_RAMAX = OFF_RI + RI_SLOTS * BLOCK_M * 8;      // [RI_SLOTS][BLOCK_M] max |r| of the row
-    static constexpr int OFF_BARS = OFF_RAMAX + RI_SLOTS * BLOCK_M * 4;
+    static constexpr int OFF_BARS = OFF_CN + 2 * BLOCK_N * 4;
     static constexpr int BYTES = OFF_BARS + 256 + 1024 /*alignment slack*/;
     static_assert(BYTES <= 227 * 1024, "shared memory budget");
     static_assert((2 * STAGES + 8) * 8 + 4 + UPD_WARPS * 4 <= 256, "barrier block");
 };
 constexpr int SMEM_BYTES = Smem<1>::BYTES > Smem<2>::BYTES ? Smem<1>::BYTES : Smem<2>::BYTES;
 
-constexpr int MAX_STACKS = 2;     // S0-S3 and A0-A3 of one tokenizer in one launch
-
-// One RVQ stack as the kernel sees it. A launch with two stacks gives the first half of the grid to stack 0 and the
-// second half to stack 1 (whole CTA pairs), so a CTA serves ONE stack for its whole life: the stack's pointers are
-// fixed per CTA, the tiles of each stack are dealt round-robin over its CTAs exactly as in a single-stack launch, and
-// two stacks balance over the SMs like one stack of twice the length. Layer 0 of a tile reads the prepared rows
-// (r0 / its fp16 operand / rowinfo0), which the update warps never write: stacks that quantise the SAME frames share
-// one layer-0 preparation.
 struct StackRef {
     const float* cbf;            // [L, K, dp] fp32 codebooks, zero padded
     const double* cn64;          // [L, K]
     const float* cn32;           // [L, kp], +inf in the padding
     const rows::LayerConst* lc;  // [L]
     const float* r0;             // [rows, dp] rows entering layer 0, written by the preparation kernel
-    const float4* rowinfo0;      // [rows] {alpha, -, window, sx} of layer 0
-    const float* rowamax0;       // [rows] max |x| of the row
-    // rows written by the update warps: the residual (layers >= 1 read it), the fp16 operand of the next layer, and
-    // {alpha, window} / max |r| for tiles of a group beyond RI_SLOTS (shared memory otherwise). With one stack they
-    // may alias the prepared rows (the update then works in place).
-    float* r_work;
-    __half* a_work;
-    float4* rowinfo_work;
-    float* rowamax_work;
+    float* r;                    // [rows, dp] residual rows written back by the update warps (may alias r0: in place)
+    __half* a;                   // [rows, dp] fp16 operand rows written by the update warps (layer 0's come from the
+                                 //   preparation kernel through its own tensor map; may be the same buffer)
+    float4* rowinfo;             // [rows] {alpha, -, window, sx}: layer 0's from the preparation kernel (rowinfo0), then
+    const float4* rowinfo0;      //   written per layer by the update warps into `rowinfo`
+    float* rowamax;              // [rows] max |r| of the row, ditto (rowamax0 / rowamax)
+    const float* rowamax0;
     void* codes;                 // [L, codes_ld] index streams
     long long codes_ld, code_off;
     double* row_loss;            // [L, loss_ld] per-frame sum of t^2, or nullptr
@@ -155,9 +127,7 @@ struct StackRef {
 };
 
 struct StackArgs {
-    StackRef s[MAX_STACKS];
-    int n_stacks;
-    int split;                   // first CTA of stack 1 (== gridDim.x when the launch has one stack); even for CTA pairs
+    StackRef s;
     int n_rows, n_tiles, K, kp, dp, code_dtype;
     int group;                   // tiles per group (>= 1); >= tiles per CTA means plain layer-major order
     int dbg_mode;                // timing experiments only (results invalid when != 0)
@@ -276,6 +246,31 @@ __device__ __forceinline__ void stg256(float* p, const F8& r) {
                  ::"l"(p), "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]), "f"(r.v[3]), "f"(r.v[4]), "f"(r.v[5]), "f"(r.v[6]), "f"(r.v[7])
                  : "memory");
 }
+// Residual rows are streamed (read once per layer, written once per stack): with an evict-first priority in L2 they
+// stop displacing the fp16 operand rows, which the TMA reads back two jobs after the update warps wrote them.
+#ifndef NAT_L2_HINTS
+#define NAT_L2_HINTS 1
+#endif
+__device__ __forceinline__ F8 ldg256_stream(const float* p) {
+#if NAT_L2_HINTS
+    F8 r;
+    asm volatile("ld.global.L1::no_allocate.L2::evict_first.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+                 : "l"(p) : "memory");
+    return r;
+#else
+    return ldcg256(p);
+#endif
+}
+__device__ __forceinline__ void stg256_stream(float* p, const F8& r) {
+#if NAT_L2_HINTS
+    asm volatile("st.global.L2::evict_first.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]), "f"(r.v[3]), "f"(r.v[4]), "f"(r.v[5]), "f"(r.v[6]), "f"(r.v[7])
+                 : "memory");
+#else
+    stg256(p, r);
+#endif
+}
 // The same update on a row held as NH groups of eight consecutive floats per lane (group g = floats (g * 32 + lane) * 8 ...).
 template <int NH>
 __device__ __forceinline__ void replay_update8(F8 (&rv)[NH], const float* __restrict__ c, int lane) {
@@ -306,6 +301,32 @@ __device__ __forceinline__ void replay_update(float4 (&rv)[NV], const float4* __
 // a - b on both halves, rounded exactly like two __fsub_rn (one fused multiply by -1, one rounding)
 __device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
 
+// Two sums and one maximum over the warp in 8 shuffles instead of 15: the lanes first split the quantities between
+// them (bit 0 of the lane: which sum; bit 1: sum or maximum), then reduce each over the lanes that hold it.
+// Results are valid in lane 0. (Shuffles travel through the same shared-memory pipe as the MMA's operand reads.)
+#ifndef NAT_REDUCE3
+#define NAT_REDUCE3 0
+#endif
+__device__ __forceinline__ void warp_reduce_2sum_1max(float& s0, float& s1, float& m, int lane) {
+#if NAT_REDUCE3
+    const bool b0 = lane & 1, b1 = lane & 2;
+    float v = (b0 ? s1 : s0) + __shfl_xor_sync(0xffffffffu, b0 ? s0 : s1, 1);       // pair sums: even lanes s0, odd lanes s1
+    float mm = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    const float recv = __shfl_xor_sync(0xffffffffu, b1 ? v : mm, 2);
+    v = b1 ? fmaxf(mm, recv) : v + recv;                                             // lanes with bit 1: the maximum
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+        const float t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = b1 ? fmaxf(v, t) : v + t;
+    }
+    s0 = v;                                                                          // lane 0: s0, lane 1: s1, lane 2: max
+    s1 = __shfl_sync(0xffffffffu, v, 1);
+    m = __shfl_sync(0xffffffffu, v, 2);
+#else
+    s0 = warp_sum(s0); s1 = warp_sum(s1); m = warp_max(m);
+#endif
+}
+
 // PAIR = 1: one CTA per tile, tcgen05.mma.cta_group::1 (M 128 x N 256).
 // PAIR = 2: launched as clusters of two CTAs (the two SMs of a TPC). Each CTA still owns its own 128-frame tiles,
 //   candidate lists, update warps and accumulators, but the pair runs ONE tcgen05.mma.cta_group::2 (M 256 x N 256)
@@ -316,14 +337,17 @@ __device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __ffma2_rn(b
 //   `tempty`.
 template <int NV, int PAIR, bool DBG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a0,  // fp16 [rows, dp], box 64 x 128, SWIZZLE_128B: layer-0 operand of stack 0
-                 const __grid_constant__ CUtensorMap map_a1,  // ditto of stack 1 (the same buffer when both stacks quantise the same frames)
-                 const __grid_constant__ CUtensorMap map_aw0, // ditto: the operand rows the update warps write (layers >= 1), stack 0
-                 const __grid_constant__ CUtensorMap map_aw1, // ditto, stack 1
-                 const __grid_constant__ CUtensorMap map_b0,  // fp16 [L*kp, dp], box 64 x (256 / PAIR), SWIZZLE_128B: codebooks of stack 0
-                 const __grid_constant__ CUtensorMap map_b1,  // ditto of stack 1
+rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a0,  // fp16 [rows, dp], box 64 x 128, SWIZZLE_128B: the prepared operand rows (layer 0)
+                 const __grid_constant__ CUtensorMap map_a,   // ditto: the operand rows the update warps write (layers >= 1)
+                 const __grid_constant__ CUtensorMap map_b,   // fp16 [L*kp, dp], box 64 x (256 / PAIR), SWIZZLE_128B: the stack's codebooks
                  const __grid_constant__ StackArgs p) {
     static_assert(PAIR == 1 || PAIR == 2, "one CTA or a CTA pair");
+    // Dependents (the next stack of the same tokenizer, launched programmatically) share nothing this kernel writes:
+    // they may take an SM as soon as one of this grid's CTAs leaves it.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const StackRef& sk = p.s;
+    const int lb = static_cast<int>(blockIdx.x);
+    const int part = static_cast<int>(gridDim.x);
     using SM = Smem<PAIR>;
     using WaitClock = WaitClockT<DBG>;
     const int dbg_mode = DBG ? p.dbg_mode : 0;
@@ -331,7 +355,6 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a0,  // fp16 [rows, dp]
     constexpr int STAGES = SM::STAGES, B_BYTES = SM::B_BYTES;
     constexpr int OFF_A = SM::OFF_A, OFF_B = SM::OFF_B, OFF_LIST_S = SM::OFF_LIST_S, OFF_LIST_I = SM::OFF_LIST_I,
                   OFF_HAND = SM::OFF_HAND, OFF_CN = SM::OFF_CN, OFF_BARS = SM::OFF_BARS;
-
     const uint32_t crank = PAIR == 2 ? cluster_ctarank() : 0u;
     const bool leader = crank == 0;
     extern __shared__ uint8_t smem_raw[];
@@ -341,10 +364,6 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a0,  // fp16 [rows, dp]
     float* list_s = reinterpret_cast<float*>(smem + OFF_LIST_S);                    // [LCAP][128]
     uint32_t* list_i = reinterpret_cast<uint32_t*>(smem + OFF_LIST_I);              // [LCAP][128] group id << 8 | mask
     uint4* hand = reinterpret_cast<uint4*>(smem + OFF_HAND);                        // [2][128] records of two uint4
-    // {alpha, window} and max |r| of the frames of the group's tiles for their NEXT layer: written by the update
-    // warps, read by the candidate warps (chunk 0) and by the update warps themselves one layer later
-    float2* const ri_s = reinterpret_cast<float2*>(smem + SM::OFF_RI);          // [RI_SLOTS][BLOCK_M]
-    float* const ramax_s = reinterpret_cast<float*>(smem + SM::OFF_RAMAX);      // [RI_SLOTS][BLOCK_M]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
     uint64_t* full = bars;                  // TMA -> MMA
     uint64_t* empty = bars + STAGES;        // MMA -> TMA
@@ -359,20 +378,14 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a0,  // fp16 [rows, dp]
     const int lane = threadIdx.x & 31;
     const int n_chunks = p.kp / BLOCK_N;
     const int n_kblocks = p.dp / BLOCK_K;
-    // This CTA's stack and its place among the stack's CTAs: tiles lb, lb + part, ... PAIR = 2: both CTAs take the
-    // leader's count, so the odd CTA may run one phantom tile (index >= n_tiles).
-    const int si = NAT_FORCE_SI0 ? 0 : (static_cast<int>(blockIdx.x) >= p.split);
-    const StackRef& sk = p.s[si];
-    const int lb = static_cast<int>(blockIdx.x) - (si ? p.split : 0);
-    const int part = si ? static_cast<int>(gridDim.x) - p.split : p.split;
+    // PAIR = 2: both CTAs take the leader's count, so the odd CTA may run one phantom tile (index >= n_tiles)
     const int my_tiles = (p.n_tiles - (lb - static_cast<int>(crank)) + part - 1) / part;
     const int group = max(1, p.group);
-    const int L = sk.L;
 
     if (warp == WARP_TMA && lane == 0) {
-        tma_prefetch_desc(si ? &map_a1 : &map_a0);
-        tma_prefetch_desc(si ? &map_aw1 : &map_aw0);
-        tma_prefetch_desc(si ? &map_b1 : &map_b0);
+        tma_prefetch_desc(&map_a0);
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
@@ -404,13 +417,11 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a0,  // fp16 [rows, dp]
         const long long t_start = w_ready.begin();
         for (int g0 = 0; g0 < my_tiles; g0 += group) {
             const int gs = min(group, my_tiles - g0);
-            for (int l = 0; l < L; ++l) {
-                const CUtensorMap* map_a = l > 0 ? (si ? &map_aw1 : &map_aw0) : (si ? &map_a1 : &map_a0);
-                const CUtensorMap* map_b = si ? &map_b1 : &map_b0;
+            for (int l = 0; l < sk.L; ++l) {
+                const CUtensorMap* map_al = l == 0 ? &map_a0 : &map_a;
                 for (int i = g0; i < g0 + gs; ++i, ++job) {
                     // a phantom tile re-reads the last real tile's operand (its results are never used)
                     const int tile = min(lb + i * part, p.n_tiles - 1);
-                    const int arow = tile * BLOCK_M;
                     if (l > 0) {
                         const long long t0 = w_ready.begin();
                         // operand rows of (tile, l) are written by this CTA's update warps in job (tile, l-1):
@@ -432,13 +443,13 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a0,  // fp16 [rows, dp]
                                     if (leader) mbar_arrive_expect_tx(&full[s], 2 * ((skip_a ? 0 : A_STAGE_BYTES) + B_BYTES));
                                     const uint32_t bar = mapa_rank(smem_u32(&full[s]), 0);
                                     if (!skip_a)
-                                    tma_load_2d_pair(smem_a + s * A_STAGE_BYTES, map_a, bar, kb * BLOCK_K, arow);
-                                    tma_load_2d_pair(smem_b + s * B_BYTES, map_b, bar, kb * BLOCK_K,
+                                    tma_load_2d_pair(smem_a + s * A_STAGE_BYTES, map_al, bar, kb * BLOCK_K, tile * BLOCK_M);
+                                    tma_load_2d_pair(smem_b + s * B_BYTES, &map_b, bar, kb * BLOCK_K,
                                                      l * p.kp + chunk * BLOCK_N + crank * (BLOCK_N / 2));
                                 } else {
                                     mbar_arrive_expect_tx(&full[s], A_STAGE_BYTES + B_BYTES);
-                                    tma_load_2d(smem_a + s * A_STAGE_BYTES, map_a, &full[s], kb * BLOCK_K, arow);
-                                    tma_load_2d(smem_b + s * B_BYTES, map_b, &full[s], kb * BLOCK_K,
+                                    tma_load_2d(smem_a + s * A_STAGE_BYTES, map_al, &full[s], kb * BLOCK_K, tile * BLOCK_M);
+                                    tma_load_2d(smem_b + s * B_BYTES, &map_b, &full[s], kb * BLOCK_K,
                                                 l * p.kp + chunk * BLOCK_N);
                                 }
                                 if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -460,7 +471,7 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a0,  // fp16 [rows, dp]
         if (lane == 0 && leader) {
             constexpr uint32_t idesc = umma_idesc_f16_f32(BLOCK_M * PAIR, BLOCK_N);
             uint32_t s = 0, ph = 0;
-            const int total = L * my_tiles * n_chunks;
+            const int total = sk.L * my_tiles * n_chunks;
             WaitClock w_tempty(dbg_out != nullptr), w_full(dbg_out != nullptr);
             for (int it = 0; it < total; ++it) {
                 const uint32_t as = it & 1, aph = (it >> 1) & 1;
@@ -520,7 +531,7 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a0,  // fp16 [rows, dp]
         const long long t_epi = w_tfull.begin();
         for (int g0 = 0; g0 < my_tiles; g0 += group) {
             const int gs = min(group, my_tiles - g0);
-            for (int l = 0; l < L; ++l) {
+            for (int l = 0; l < sk.L; ++l) {
                 for (int i = g0; i < g0 + gs; ++i, ++job) {
                     const int tile = lb + i * part;
                     const long long row = static_cast<long long>(tile) * BLOCK_M + tid;
@@ -547,37 +558,24 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a0,  // fp16 [rows, dp]
                         cnt = w;
                     };
 
-                    // layer 0: written by the preparation kernel (fetched before the wait); later layers: left in shared
-                    // memory by this CTA's update warps one layer ago, known to be there once the accumulators are
-                    const bool ri_global = !NAT_RI_SMEM || l == 0 || i - g0 >= RI_SLOTS;
-                    if (l == 0 && valid) {
-                        const float4 ri = __ldcg(sk.rowinfo0 + row);
-                        alpha = ri.x;
-                        window = ri.z;
-                    }
                     for (int chunk = 0; chunk < n_chunks; ++chunk, ++it) {
                         const uint32_t as = it & 1, aph = (it >> 1) & 1;
                         const long long t0 = w_tfull.begin();
                         mbar_wait(&tfull[as], aph);
                         w_tfull.end(t0);
                         tcgen05_fence_after();
-                        if (chunk == 0 && valid && l > 0) {
-                            if (ri_global) {
-                                const float4 ri = __ldcg(sk.rowinfo_work + row);
-                                alpha = ri.x;
-                                window = ri.z;
-                            } else {
-                                const float2 ri = ri_s[(i - g0) * BLOCK_M + tid];
-                                alpha = ri.x;
-                                window = ri.y;
-                            }
+                        if (chunk == 0 && valid) {
+                            // written by this CTA's update warps one layer ago: only now is it known to be there
+                            const float4 ri = __ldcg((l == 0 ? sk.rowinfo0 : sk.rowinfo) + row);
+                            alpha = ri.x;
+                            window = ri.z;
                         }
                         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N;
                         // (layer, chunk) after this one in the job sequence; past the end it wraps to (0, 0)
                         int nl = l, nchunk = chunk + 1;
                         if (nchunk == n_chunks) {
                             nchunk = 0;
-                            if (i + 1 >= g0 + gs) nl = (l + 1 < L) ? l + 1 : 0;
+                            if (i + 1 >= g0 + gs) nl = (l + 1 < sk.L) ? l + 1 : 0;
                         }
                         const float2 cn_next = __ldg(reinterpret_cast<const float2*>(
                                                          sk.cn32 + static_cast<long long>(nl) * p.kp + nchunk * BLOCK_N) + tid);
@@ -585,66 +583,6 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a0,  // fp16 [rows, dp]
                         const uint32_t cn_s = cnbuf + (it & 1) * (BLOCK_N * 4);
                         const int gid0 = (chunk * BLOCK_N) >> 3;
 
-#if NAT_SCAN_RECOMPUTE
-                        // filter = false: running minimum only.  filter = true: minimum + list of groups in the window.
-                        // The four eight-group minima are formed first (packed FFMA2: two scores per instruction), and ONE
-                        // test against the threshold guards the list code: thr only ever shrinks, so a block whose
-                        // smallest score is above it has no entry to add. Inside, the groups are taken in order with the
-                        // threshold updated after each entry, exactly as if they had been tested one by one; the eight
-                        // scores of a listed group are formed again there (same instructions, same bits) rather than
-                        // kept alive across the whole block, which is what lets this role live in 64 registers.
-                        const float2 alpha2 = make_float2(alpha, alpha);
-                        auto scores8 = [&](const uint32_t (&v)[32], int g, int h, float2 (&s2)[4]) {
-                            const float4 c0 = lds_f32x4(cn_s + (g * 32 + h * 8) * 4);
-                            const float4 c1 = lds_f32x4(cn_s + (g * 32 + h * 8 + 4) * 4);
-                            s2[0] = __ffma2_rn(make_float2(__uint_as_float(v[h * 8 + 0]), __uint_as_float(v[h * 8 + 1])), alpha2, make_float2(c0.x, c0.y));
-                            s2[1] = __ffma2_rn(make_float2(__uint_as_float(v[h * 8 + 2]), __uint_as_float(v[h * 8 + 3])), alpha2, make_float2(c0.z, c0.w));
-                            s2[2] = __ffma2_rn(make_float2(__uint_as_float(v[h * 8 + 4]), __uint_as_float(v[h * 8 + 5])), alpha2, make_float2(c1.x, c1.y));
-                            s2[3] = __ffma2_rn(make_float2(__uint_as_float(v[h * 8 + 6]), __uint_as_float(v[h * 8 + 7])), alpha2, make_float2(c1.z, c1.w));
-                        };
-                        auto scan32 = [&](const uint32_t (&v)[32], int g, bool filter) {
-                            float mn[4];
-#pragma unroll
-                            for (int h = 0; h < 4; ++h) {
-                                float2 s2[4];
-                                scores8(v, g, h, s2);
-                                mn[h] = fminf(fminf(fminf(fminf(s2[0].x, s2[0].y), s2[1].x),
-                                                    fminf(fminf(s2[1].y, s2[2].x), s2[2].y)),
-                                              fminf(fminf(s2[3].x, s2[3].y), inf));
-                            }
-                            const float mall = fminf(fminf(mn[0], mn[1]), fminf(mn[2], mn[3]));
-                            if (!filter) {
-                                m = fminf(m, mall);
-                                return;
-                            }
-                            if (!(mall <= thr)) return;
-#pragma unroll
-                            for (int h = 0; h < 4; ++h) {
-                                if (mn[h] <= thr) {
-                                    if (DBG) ++n_events;
-                                    m = fminf(m, mn[h]);
-                                    // m + W rounded up: the kept set must be a superset of the exact window
-                                    thr = fmaf(fabsf(m) + window, 2.4e-7f, m + window);
-                                    float2 s2[4];
-                                    scores8(v, g, h, s2);
-                                    uint32_t mask = 0;
-#pragma unroll
-                                    for (int e = 0; e < 4; ++e)
-                                        mask |= ((s2[e].x <= thr) ? (1u << (2 * e)) : 0u) | ((s2[e].y <= thr) ? (2u << (2 * e)) : 0u);
-                                    if (cnt == LCAP) compact();
-                                    if (cnt < LCAP) {
-                                        sts_f32(ls + cnt * (BLOCK_M * 4), mn[h]);
-                                        sts_u32(li + cnt * (BLOCK_M * 4),
-                                                (static_cast<uint32_t>(gid0 + g * 4 + h) << 8) | mask);
-                                        ++cnt;
-                                    } else {
-                                        overflow = true;
-                                    }
-                                }
-                            }
-                        };
-
-#else
                         // FILTER = false: running minimum only.  FILTER = true: minimum + list of groups in the window.
                         // All 32 scores and the four eight-group minima are formed first (independent instructions), and
                         // ONE test against the threshold guards the list code: thr only ever shrinks, so a block whose
@@ -698,7 +636,6 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a0,  // fp16 [rows, dp]
                             }
                         };
 
-#endif
                         uint32_t va[32];
                         if (chunk == 0) {
 #pragma unroll 1
@@ -765,12 +702,10 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a0,  // fp16 [rows, dp]
         else if (REGS_UPD < LAUNCH_REGS) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_UPD));
         // ------------------------------------------------------------------ update: one warp per frame
         // Phase 0 settles the frames the coarse pass could not certify (exact fp64 re-rank, or the exact scan).
-        // Phase 1 is a software pipeline over the warp's rows: as soon as a register group of row rr has been used,
-        // the same registers receive row rr+1's residual and code vector, so the loads of the next row travel under
-        // the arithmetic, the stores and the warp reductions of this one. The operand scale of the next layer comes
-        // from a bound (max|r| + max|c|), not from the new row, so no element waits on a reduction; the exact new max
-        // is reduced afterwards and kept for the next layer's bound. The codes a replay needs (layers whose residual
-        // was not written back) are fetched at the start of the job, before the wait for the candidates.
+        // Phase 1 is branch-free: row rr+1's residual and code vector are in flight while row rr is updated, and the
+        // warp reductions + error window of row rr-1 are scheduled under row rr's arithmetic. The operand scale of
+        // the next layer comes from a bound (max|r| + max|c|), not from the new row, so no element waits on a
+        // reduction; the exact new max is reduced afterwards and kept for the next layer's bound.
         const int uw = warp - WARP_UPD0;
         const int dp4 = p.dp >> 2;
         uint32_t job = 0;
@@ -778,10 +713,10 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a0,  // fp16 [rows, dp]
         const long long t_upd = w_cfull.begin();
         for (int g0 = 0; g0 < my_tiles; g0 += group) {
             const int gs = min(group, my_tiles - g0);
-            for (int l = 0; l < L; ++l) {
+            for (int l = 0; l < sk.L; ++l) {
                 const float* cb_l = sk.cbf + static_cast<long long>(l) * p.K * p.dp;
                 const double* cn64_l = sk.cn64 + static_cast<long long>(l) * p.K;
-                const bool last = l + 1 == L;
+                const bool last = l + 1 == sk.L;
                 const rows::LayerConst* lc_next = last ? nullptr : sk.lc + l + 1;
                 const float cabs = __ldg(&sk.lc[l].cabs);
                 double* loss_l = sk.row_loss != nullptr ? sk.row_loss + static_cast<long long>(l) * sk.loss_ld : nullptr;
@@ -791,47 +726,19 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a0,  // fp16 [rows, dp]
                 const int store_mask = (sk.row_loss == nullptr && dp4 == NV * 32) ? sk.store_mask : ~0;
                 int n_replay = 0;
                 for (int jj = l - 1; jj >= 0 && !((store_mask >> jj) & 1); --jj) ++n_replay;
-                // rows this layer reads: the prepared ones until some earlier layer of the stack has written a residual back
-                const float* r_layer = n_replay == l ? sk.r0 : sk.r_work;
+                // rows this layer reads: the prepared ones until an earlier layer of the stack has written a residual back
+                const float* r_src = n_replay == l ? sk.r0 : sk.r;
                 char* codes_l = static_cast<char*>(sk.codes);
                 const long long code_base = static_cast<long long>(l) * sk.codes_ld + sk.code_off;
                 for (int i = g0; i < g0 + gs; ++i, ++job) {
                     const int tile = lb + i * part;
                     const int row0 = tile * BLOCK_M + uw * ROWS_PER_UPD_WARP;
                     const int nrows = max(0, min(ROWS_PER_UPD_WARP, p.n_rows - row0));
-                    const long long wrow0 = row0;
-                    const float* r_src = r_layer + static_cast<long long>(row0) * p.dp;
-                    const bool ri_smem = NAT_RI_SMEM && i - g0 < RI_SLOTS;   // this tile's per-frame constants travel in shared memory
-                    const int ri_base = (i - g0) * BLOCK_M + uw * ROWS_PER_UPD_WARP;
                     float am_old = 0.f;                // lane rr: max |r| of row rr before this layer
-                    int jrep1 = 0, jrep2 = 0;          // lane rr: codes of row rr one / two layers back (replays)
-                    if (lane < nrows) {
-                        if (residual_needed)
-                            am_old = l == 0 ? __ldcg(sk.rowamax0 + row0 + lane)
-                                            : (ri_smem ? ramax_s[ri_base + lane] : __ldcg(sk.rowamax_work + wrow0 + lane));
-#if NAT_UPD_JREP
-                        if (n_replay >= 1) jrep1 = rows::load_code(codes_l, p.code_dtype, code_base - sk.codes_ld + row0 + lane);
-                        if (n_replay >= 2) jrep2 = rows::load_code(codes_l, p.code_dtype, code_base - 2 * sk.codes_ld + row0 + lane);
-#endif
-                    }
-                    // code of row rr chosen `back` layers ago (warp-uniform arguments)
-                    auto replay_code = [&](int back, int rr) -> int {
-#if NAT_UPD_JREP
-                        if (back == 1) return __shfl_sync(0xffffffffu, jrep1, rr);
-                        if (back == 2) return __shfl_sync(0xffffffffu, jrep2, rr);
-#endif
-                        return rows::load_code(codes_l, p.code_dtype, code_base - back * sk.codes_ld + row0 + rr);
-                    };
-                    const bool hot = !last && loss_l == nullptr && dp4 == NV * 32 && nrows > 0;
-                    constexpr int NH = NV / 2;                 // groups of eight floats per lane
-                    // the first row's residual does not depend on the decision: in flight before the candidates arrive
-                    F8 cur[NH];
-#if NAT_UPD_PRELOAD
-                    if (hot) {
-#pragma unroll
-                        for (int g = 0; g < NH; ++g) cur[g] = ldcg256(r_src + (g * 32 + lane) * 8);
-                    }
-#endif
+                    // (No early L2 prefetch of the residual rows here: issued a whole GEMM ahead, the lines were evicted
+                    // again before use and cost a second DRAM read; measured 4.6 % slower. A late one, issued when the
+                    // job's candidates arrive, measured 4.6 % slower than none as well.)
+                    if (residual_needed && nrows > 0 && lane < nrows) am_old = __ldcg((l == 0 ? sk.rowamax0 : sk.rowamax) + row0 + lane);
                     const uint32_t slot = job & 1;
                     const long long t0 = w_cfull.begin();
                     mbar_wait(&cfull[slot], (job >> 1) & 1);
@@ -867,13 +774,16 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a0,  // fp16 [rows, dp]
                             return static_cast<int>(((c + 1) & 1) ? (word >> 16) : (word & 0xFFFFu));
                         };
                         float4 rv[NV];
-                        load_row<NV>(rv, reinterpret_cast<const float4*>(r_src + static_cast<long long>(rr) * p.dp), dp4, lane);
+                        load_row<NV>(rv, reinterpret_cast<const float4*>(r_src + static_cast<long long>(row0 + rr) * p.dp), dp4, lane);
+                        if constexpr (true) {
 #pragma unroll 1
-                        for (int back = n_replay; back > 0; --back) {
-                            const int jp = replay_code(back, rr);
-                            if (dp4 == NV * 32)
-                                replay_update<NV>(rv, reinterpret_cast<const float4*>(
-                                    cb_l + (static_cast<long long>(jp) - static_cast<long long>(back) * p.K) * p.dp), lane);
+                            for (int back = n_replay; back > 0; --back) {
+                                const int jp = rows::load_code(codes_l, p.code_dtype,
+                                                               code_base - back * sk.codes_ld + row0 + rr);
+                                if (dp4 == NV * 32)
+                                    replay_update<NV>(rv, reinterpret_cast<const float4*>(
+                                        cb_l + (static_cast<long long>(jp) - static_cast<long long>(back) * p.K) * p.dp), lane);
+                            }
                         }
                         double best = 0.0;
                         int bestj = -1;
@@ -890,7 +800,6 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a0,  // fp16 [rows, dp]
                             }
                             ++n_scan;
                         } else {
-#if !NAT_UPD_PAIR_RERANK
 #pragma unroll 1
                             for (int c = 0; c < static_cast<int>(n); ++c) {        // warp-uniform trip count, <= HCAP
                                 const int k = min(candidate(c), p.K - 1);
@@ -898,21 +807,6 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a0,  // fp16 [rows, dp]
                                                                 dp4, cn64_l[k], lane);
                                 if (bestj < 0 || s < best || (s == best && k < bestj)) { best = s; bestj = k; }
                             }
-#else
-                            // two candidates per step: both code vectors are in flight together
-#pragma unroll 1
-                            for (int c = 0; c < static_cast<int>(n); c += 2) {     // warp-uniform trip count, n <= HCAP
-                                const bool two = c + 1 < static_cast<int>(n);
-                                const int k0 = min(candidate(c), p.K - 1);
-                                const int k1 = two ? min(candidate(c + 1), p.K - 1) : k0;
-                                const double s0 = score_regs<NV>(rv, reinterpret_cast<const float4*>(cb_l + static_cast<long long>(k0) * p.dp),
-                                                                 dp4, cn64_l[k0], lane);
-                                const double s1 = score_regs<NV>(rv, reinterpret_cast<const float4*>(cb_l + static_cast<long long>(k1) * p.dp),
-                                                                 dp4, cn64_l[k1], lane);
-                                if (bestj < 0 || s0 < best || (s0 == best && k0 < bestj)) { best = s0; bestj = k0; }
-                                if (two && (s1 < best || (s1 == best && k1 < bestj))) { best = s1; bestj = k1; }
-                            }
-#endif
                             ++n_rerank;
                         }
                         if (lane == rr) jsel = bestj;
@@ -923,66 +817,39 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a0,  // fp16 [rows, dp]
                     w_dec.end(tA);
                     // ---- phase 1: residual update, next operand, error window
                     const long long tB = w_res.begin();
-                    // this row's {alpha, window} and max |r| for the next layer: shared memory for the group's tiles
-                    auto publish_rowinfo = [&](int rr, int row, const float4& ri, float amx) {
-                        if (ri_smem) {
-                            ri_s[ri_base + rr] = make_float2(ri.x, ri.z);
-                            ramax_s[ri_base + rr] = amx;
-                        } else {
-                            sk.rowinfo_work[wrow0 + rr] = ri;
-                            sk.rowamax_work[wrow0 + rr] = amx;
-                        }
-                    };
-                    if (hot) {
+                    if (!last && loss_l == nullptr && dp4 == NV * 32 && nrows > 0) {
                         // Hot form: every lane holds exactly NV / 2 groups of eight consecutive floats of a row (256-bit
-                        // loads and stores), nothing is predicated.
+                        // loads and stores), nothing is predicated. One row at a time per warp; the sixteen update warps
+                        // of the CTA cover each other's memory latency.
                         // The residual entering the LAST layer is only ever seen through its fp16 operand (the last
                         // layer emits codes and, without a loss, nothing else): it is not written back.
                         const bool keep_r = (store_mask >> l) & 1;
-                        F8 cv[NH];
-#if NAT_UPD_PIPELINE
-                        {
-#if !NAT_UPD_PRELOAD
-#pragma unroll
-                            for (int g = 0; g < NH; ++g) cur[g] = ldcg256(r_src + (g * 32 + lane) * 8);
-#endif
-                            const float* crow0 = cb_l + static_cast<long long>(__shfl_sync(0xffffffffu, jsel, 0)) * p.dp;
-#pragma unroll
-                            for (int g = 0; g < NH; ++g) cv[g] = ldcg256(crow0 + (g * 32 + lane) * 8);
-                        }
-#endif
 #pragma unroll 1
                         for (int rr = 0; rr < nrows; ++rr) {
                             const int row = row0 + rr;
-                            const float* rsrc_row = r_src + static_cast<long long>(rr) * p.dp;
-                            float* rrow = sk.r_work + (wrow0 + rr) * p.dp;
-#if NAT_UPD_PIPELINE
-                            const bool more = rr + 1 < nrows;
-                            const float* crow_next = cb_l + static_cast<long long>(__shfl_sync(0xffffffffu, jsel, more ? rr + 1 : rr)) * p.dp;
-#else
-                            const float* crow = cb_l + static_cast<long long>(__shfl_sync(0xffffffffu, jsel, rr)) * p.dp;
-#if NAT_UPD_PRELOAD
-                            if (rr > 0)
-#endif
-                            {
+                            const int j = __shfl_sync(0xffffffffu, jsel, rr);
+                            constexpr int NH = NV / 2;                 // groups of eight floats per lane
+                            float* rrow = sk.r + static_cast<long long>(row) * p.dp;
+                            const float* crow = cb_l + static_cast<long long>(j) * p.dp;
+                            F8 cur[NH], cv[NH];
 #pragma unroll
-                                for (int g = 0; g < NH; ++g) cur[g] = ldcg256(rsrc_row + (g * 32 + lane) * 8);
-                            }
-#endif
+                            for (int g = 0; g < NH; ++g)
+                                if (!(dbg_mode & 128)) cur[g] = ldg256_stream(r_src + static_cast<long long>(row) * p.dp + (g * 32 + lane) * 8);
+                                else for (int e = 0; e < 8; ++e) cur[g].v[e] = 1.f;          // timing experiment only
 #pragma unroll 1
                             for (int back = n_replay; back > 0; --back) {
-                                const int jp = replay_code(back, rr);
+                                const int jp = rows::load_code(codes_l, p.code_dtype, code_base - back * sk.codes_ld + row);
                                 replay_update8<NH>(cur, cb_l + (static_cast<long long>(jp) - static_cast<long long>(back) * p.K) * p.dp, lane);
                             }
-#if !NAT_UPD_PIPELINE
 #pragma unroll
-                            for (int g = 0; g < NH; ++g) cv[g] = ldcg256(crow + (g * 32 + lane) * 8);
-#endif
+                            for (int g = 0; g < NH; ++g)
+                                if (!(dbg_mode & 32)) cv[g] = ldcg256(crow + (g * 32 + lane) * 8);
+                                else for (int e = 0; e < 8; ++e) cv[g].v[e] = 0.5f;          // timing experiment only
                             // operand scale from the bound  max|r'| <= max|r| + max|c|
                             const float bound = (__shfl_sync(0xffffffffu, am_old, rr) + cabs) * 1.00001f;
                             const float sx = rows::pow2_scale_for(bound);
                             const float2 sx2 = make_float2(sx, sx);
-                            uint4* a_row = reinterpret_cast<uint4*>(sk.a_work + (wrow0 + rr) * p.dp);
+                            uint4* a_row = reinterpret_cast<uint4*>(sk.a + static_cast<long long>(row) * p.dp);
                             float2 lo2v = make_float2(0.f, 0.f), xh2v = make_float2(0.f, 0.f);
                             float amax = 0.f;
 #pragma unroll
@@ -1005,26 +872,15 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a0,  // fp16 [rows, dp]
                                     xh2v = __ffma2_rn(s2, s2, xh2v);
                                     hp[e] = *reinterpret_cast<const uint32_t*>(&h2);
                                 }
-#if NAT_UPD_PIPELINE == 1
-                                // this register group is free again: the next row's residual and code vector take it
-                                if (more) {
-                                    cur[g] = ldcg256(rsrc_row + p.dp + (g * 32 + lane) * 8);
-                                    cv[g] = ldcg256(crow_next + (g * 32 + lane) * 8);
-                                }
-#endif
-                                if (keep_r) stg256(rrow + (g * 32 + lane) * 8, nr);
-                                a_row[g * 32 + lane] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+                                if (keep_r && !(dbg_mode & 64)) stg256_stream(rrow + (g * 32 + lane) * 8, nr);
+                                if (!(dbg_mode & 64)) a_row[g * 32 + lane] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
                             }
-#if NAT_UPD_PIPELINE == 2
-                            if (more) {
-#pragma unroll
-                                for (int g = 0; g < NH; ++g) cur[g] = ldcg256(rsrc_row + p.dp + (g * 32 + lane) * 8);
-#pragma unroll
-                                for (int g = 0; g < NH; ++g) cv[g] = ldcg256(crow_next + (g * 32 + lane) * 8);
+                            float lo2 = lo2v.x + lo2v.y, xh2 = xh2v.x + xh2v.y, amx = amax;
+                            warp_reduce_2sum_1max(lo2, xh2, amx, lane);
+                            if (lane == 0) {
+                                sk.rowinfo[row] = rows::make_rowinfo_bound(sx, lo2, xh2, lc_next, p.dp);
+                                sk.rowamax[row] = amx;
                             }
-#endif
-                            const float lo2 = warp_sum(lo2v.x + lo2v.y), xh2 = warp_sum(xh2v.x + xh2v.y), amx = warp_max(amax);
-                            if (lane == 0) publish_rowinfo(rr, row, rows::make_rowinfo_bound(sx, lo2, xh2, lc_next, p.dp), amx);
                         }
                     } else
                     if (residual_needed && nrows > 0) {
@@ -1033,14 +889,14 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a0,  // fp16 [rows, dp]
                         for (int rr = 0; rr < nrows; ++rr) {
                             const int row = row0 + rr;
                             const int j = __shfl_sync(0xffffffffu, jsel, rr);
-                            float4* r4 = reinterpret_cast<float4*>(sk.r_work + (wrow0 + rr) * p.dp);
-                            float4 cur4[NV], cv[NV];
-                            load_row<NV>(cur4, reinterpret_cast<const float4*>(r_src + static_cast<long long>(rr) * p.dp), dp4, lane);
+                            float4* r4 = reinterpret_cast<float4*>(sk.r + static_cast<long long>(row) * p.dp);
+                            float4 cur[NV], cv[NV];
+                            load_row<NV>(cur, reinterpret_cast<const float4*>(r_src + static_cast<long long>(row) * p.dp), dp4, lane);
                             load_code<NV>(cv, reinterpret_cast<const float4*>(cb_l + static_cast<long long>(j) * p.dp), dp4, lane);
                             const float bound = (__shfl_sync(0xffffffffu, am_old, rr) + cabs) * 1.00001f;
                             const float sx = rows::pow2_scale_for(bound);
                             const float2 sx2 = make_float2(sx, sx);
-                            uint2* a_row = reinterpret_cast<uint2*>(sk.a_work + (wrow0 + rr) * p.dp);
+                            uint2* a_row = reinterpret_cast<uint2*>(sk.a + static_cast<long long>(row) * p.dp);
                             float2 lo2v = make_float2(0.f, 0.f), xh2v = make_float2(0.f, 0.f);
                             float amax = 0.f;
                             double loss = 0.0;
@@ -1048,7 +904,7 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a0,  // fp16 [rows, dp]
                             for (int k = 0; k < NV; ++k) {
                                 const int qq = k * 32 + lane;
                                 if (qq < dp4) {
-                                    const float2 x01 = make_float2(cur4[k].x, cur4[k].y), x23 = make_float2(cur4[k].z, cur4[k].w);
+                                    const float2 x01 = make_float2(cur[k].x, cur[k].y), x23 = make_float2(cur[k].z, cur[k].w);
                                     const float2 c01 = make_float2(cv[k].x, cv[k].y), c23 = make_float2(cv[k].z, cv[k].w);
                                     const float2 t01 = sub2(c01, x01), t23 = sub2(c23, x23);
                                     const float2 n01 = sub2(x01, __fadd2_rn(x01, t01)), n23 = sub2(x23, __fadd2_rn(x23, t23));
@@ -1081,14 +937,19 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a0,  // fp16 [rows, dp]
                             }
                             if (!last) {
                                 const float lo2 = warp_sum(lo2v.x + lo2v.y), xh2 = warp_sum(xh2v.x + xh2v.y), amx = warp_max(amax);
-                                if (lane == 0) publish_rowinfo(rr, row, rows::make_rowinfo_bound(sx, lo2, xh2, lc_next, p.dp), amx);
+                                if (lane == 0) {
+                                    sk.rowinfo[row] = rows::make_rowinfo_bound(sx, lo2, xh2, lc_next, p.dp);
+                                    sk.rowamax[row] = amx;
+                                }
                             }
                         }
                     }
                     w_res.end(tB);
                     // publish this warp's share of the job: global writes -> visible to the TMA (async proxy)
                     const long long tD = w_fence.begin();
-                    __threadfence();
+                    // fence.proxy.async carries a GPU-scope barrier of its own (MEMBAR.ALL.GPU + FENCE.VIEW.ASYNC): the rows
+                    // are in L2, where the TMA reads them, when the counter moves. (A __threadfence in front of it would
+                    // add a second barrier and invalidate the SM's whole L1 -- CCTL.IVALL -- every job.)
                     fence_proxy_async();
                     __syncwarp();
                     w_fence.end(tD);

@@ -58,6 +58,23 @@ class MelSpectrogram(nn.Module):
         self.log_mel = log_mel
         self.register_buffer("fb", htk_filterbank(sample_rate, n_fft, n_mels), persistent=False)
         self.last_log_mel = None
+        self._banded = {}            # device -> (filterbank version, banded form prepared once by the library)
+
+    def _banded_filterbank(self, dev):
+        """The filterbank is a constant of the transform: its banded form (what the kernel reads) is derived once per
+        device, again only if someone writes into `fb`."""
+        lib = _lib.load()
+        fb = self.fb if self.fb.device == dev else self.fb.to(dev)
+        key = (fb.data_ptr(), fb._version)
+        hit = self._banded.get(dev)
+        if hit is None or hit[0] != key:
+            buf = torch.empty(lib.nat_mel_filterbank_bytes(self.n_mels), dtype=torch.uint8, device=dev)
+            fbc = fb.contiguous()
+            _lib.check(lib.nat_mel_filterbank_prepare(fbc.data_ptr(), self.n_mels, buf.data_ptr(),
+                                                      torch.cuda.current_stream(dev).cuda_stream))
+            hit = (key, buf, fb)
+            self._banded[dev] = hit
+        return hit[1]
 
     def forward(self, waveform: torch.Tensor) -> torch.Tensor:
         lib = _lib.load()
@@ -72,15 +89,15 @@ class MelSpectrogram(nn.Module):
         if S <= self.n_fft // 2:
             raise RuntimeError(f"reflect padding of {self.n_fft // 2} needs a longer input than {S} samples")
         dev = w.device
-        fb = self.fb if self.fb.device == dev else self.fb.to(dev)
         T = lib.nat_mel_num_frames(S, self.hop_length)
         mel = torch.empty((B, self.n_mels, T), dtype=torch.float32, device=dev)
         logmel = torch.empty_like(mel) if self.log_mel else None
         with torch.cuda.device(dev):
-            _lib.check(lib.nat_mel_power_f32(w.data_ptr(), B, S, self.sample_rate, self.n_fft, self.hop_length,
-                                             self.n_mels, fb.contiguous().data_ptr(), mel.data_ptr(),
-                                             logmel.data_ptr() if logmel is not None else None,
-                                             torch.cuda.current_stream(dev).cuda_stream))
+            banded = self._banded_filterbank(dev)
+            _lib.check(lib.nat_mel_power_banded_f32(w.data_ptr(), B, S, self.sample_rate, self.n_fft, self.hop_length,
+                                                    self.n_mels, banded.data_ptr(), mel.data_ptr(),
+                                                    logmel.data_ptr() if logmel is not None else None,
+                                                    torch.cuda.current_stream(dev).cuda_stream))
         self.last_log_mel = logmel.reshape(lead + (self.n_mels, T)) if logmel is not None else None
         return mel.reshape(lead + (self.n_mels, T))
 

@@ -9,10 +9,10 @@
 
 int main() {
     using namespace nat::fe;
-    std::vector<float2> tw(NFFT / 2);
-    for (int k = 0; k < NFFT / 2; ++k) {
-        const double a = -2.0 * M_PI * k / NFFT;
-        tw[k] = make_float2((float)std::cos(a), (float)std::sin(a));
+    std::vector<float2> tw1(TW1_ELEMS), tw2(TW2_ELEMS);
+    for (int k = 1; k < 16; ++k) {
+        for (int t = 0; t < TEAM; ++t) tw1[(k - 1) * TEAM + t] = fft_twiddle_value((long long)t * k, NFFT);
+        for (int n2 = 0; n2 < 8; ++n2) tw2[(k - 1) * 8 + n2] = fft_twiddle_value((long long)n2 * k, 128);
     }
     std::vector<float2> x(NFFT);
     srand(7);
@@ -21,9 +21,9 @@ int main() {
     for (int t = 0; t < TEAM; ++t) {
         float2 a[16];
         for (int n = 0; n < 16; ++n) a[n] = x[n * TEAM + t];
-        fft_pass1(S.data(), tw.data(), t, a);
+        fft_pass1(S.data(), tw1.data(), t, a);
     }
-    for (int t = 0; t < TEAM; ++t) fft_pass2(S.data(), tw.data(), t);
+    for (int t = 0; t < TEAM; ++t) fft_pass2(S.data(), tw2.data(), t);
     std::vector<float2> ra(TEAM * 8), rb(TEAM * 8);
     for (int t = 0; t < TEAM; ++t) {
         float2 a[8], b[8];
@@ -50,6 +50,28 @@ int main() {
         max_err = std::fmax(max_err, std::hypot(S[pos].x - re, S[pos].y - im));
         max_ref = std::fmax(max_ref, std::hypot(re, im));
     }
+    // every 8-byte exchange pattern of a half-warp (16 consecutive threads) covers 16 distinct bank pairs
+    auto conflict_free = [](int (*addr)(int t, int j), int n_j, const char* what) {
+        for (int j = 0; j < n_j; ++j)
+            for (int t0 = 0; t0 < TEAM; t0 += 16) {
+                int seen = 0;
+                for (int t = t0; t < t0 + 16; ++t) {
+                    const int bank = addr(t, j) & 15;
+                    if (seen & (1 << bank)) { printf("FAIL: %s bank conflict (j=%d, t0=%d)\n", what, j, t0); return false; }
+                    seen |= 1 << bank;
+                }
+            }
+        return true;
+    };
+    bool ok = true;
+    ok &= conflict_free([](int t, int k) { return fft_phys(k * 128 + t); }, 16, "pass-1 store");
+    ok &= conflict_free([](int t, int n) { return fft_phys((t >> 3) * 128 + 8 * n + (t & 7)); }, 16, "pass-2 load/store");
+    ok &= conflict_free([](int t, int n) { return fft_phys(t * 8 + n); }, 8, "pass-3 load a");
+    ok &= conflict_free([](int t, int n) { return fft_phys((t + TEAM) * 8 + n); }, 8, "pass-3 load b");
+    ok &= conflict_free([](int t, int k3) { return fft_pos((t >> 4) + 16 * (t & 15) + 256 * k3); }, 8, "pass-3 store a");
+    ok &= conflict_free([](int t, int k3) { return fft_pos((t >> 4) + 16 * (t & 15) + 8 + 256 * k3); }, 8, "pass-3 store b");
+    ok &= conflict_free([](int t, int k) { return k * TEAM + t; }, 15, "pass-1 twiddles");
+    if (!ok) return 1;
     printf("max_err %.3e max_ref %.3e rel %.3e\n", max_err, max_ref, max_err / max_ref);
     if (!(max_err <= 2e-6 * max_ref)) { printf("FAIL\n"); return 1; }
     printf("OK\n");
