@@ -219,6 +219,8 @@ struct nat_rvq_codebooks {
     float* cbf;                       // [L, K, dp]
     __half* cbh;                      // [L, kp, dp]
     float* cn32;                      // [L, kp]
+    float* cn32m;                     // [L, kp] the same with later exact duplicates masked (+inf): the argmin paths
+    unsigned long long* row_hash;     // [K] scratch of the duplicate search
     double* cn64;                     // [L, K]
     nat::rows::LayerConst* lc;        // [L]
     int* scratch;                     // [L, kScratchPerLayer]
@@ -272,6 +274,14 @@ static int upload_codebooks(nat_rvq_codebooks* cb, const float* const* codebooks
             dst, cb->K, cb->kp, cb->dp, cb->cbh + static_cast<long long>(l) * cb->kp * cb->dp,
             cb->cn32 + static_cast<long long>(l) * cb->kp, cb->cn64 + static_cast<long long>(l) * cb->K, scr));
     }
+    for (int l = 0; l < cb->L; ++l) {
+        const float* src = cb->cbf + static_cast<long long>(l) * cb->K * cb->dp;
+        const int grid = std::min((cb->K + 7) / 8, 148 * 8);
+        NAT_LAUNCH(6, st, prepare::row_hash_kernel<<<grid, 256, 0, st>>>(src, cb->K, cb->dp, cb->row_hash));
+        NAT_LAUNCH(6, st, prepare::mask_duplicates_kernel<<<std::min((cb->kp + 7) / 8, 148 * 8), 256, 0, st>>>(
+            src, cb->row_hash, cb->cn32 + static_cast<long long>(l) * cb->kp, cb->cn32m + static_cast<long long>(l) * cb->kp,
+            cb->K, cb->kp, cb->dp));
+    }
     NAT_LAUNCH(6, st, prepare::finish_consts_kernel<<<1, 32, 0, st>>>(cb->scratch, cb->L, cb->lc));
     NAT_CUDA(cudaGetLastError());
     return NAT_OK;
@@ -301,6 +311,8 @@ int nat_rvq_codebooks_create(const float* const* codebooks_dev, int L, int K, in
     if (rc == NAT_OK) guard(cudaMalloc(&cb->cbf, n_f * 4), "cudaMalloc(cbf)");
     if (rc == NAT_OK) guard(cudaMalloc(&cb->cbh, n_h * 2), "cudaMalloc(cbh)");
     if (rc == NAT_OK) guard(cudaMalloc(&cb->cn32, static_cast<size_t>(L) * cb->kp * 4), "cudaMalloc(cn32)");
+    if (rc == NAT_OK) guard(cudaMalloc(&cb->cn32m, static_cast<size_t>(L) * cb->kp * 4), "cudaMalloc(cn32m)");
+    if (rc == NAT_OK) guard(cudaMalloc(&cb->row_hash, static_cast<size_t>(K) * 8), "cudaMalloc(row_hash)");
     if (rc == NAT_OK) guard(cudaMalloc(&cb->cn64, static_cast<size_t>(L) * K * 8), "cudaMalloc(cn64)");
     if (rc == NAT_OK) guard(cudaMalloc(&cb->lc, sizeof(nat::rows::LayerConst) * L), "cudaMalloc(lc)");
     if (rc == NAT_OK) guard(cudaMalloc(&cb->scratch, sizeof(int) * L * nat::prepare::kScratchPerLayer), "cudaMalloc");
@@ -358,7 +370,8 @@ int nat_rvq_codebooks_update(nat_rvq_codebooks* cb, const float* const* codebook
 
 int nat_rvq_codebooks_destroy(nat_rvq_codebooks* cb) {
     if (cb == nullptr) return NAT_OK;
-    cudaFree(cb->cbf); cudaFree(cb->cbh); cudaFree(cb->cn32); cudaFree(cb->cn64); cudaFree(cb->lc);
+    cudaFree(cb->cbf); cudaFree(cb->cbh); cudaFree(cb->cn32); cudaFree(cb->cn32m); cudaFree(cb->row_hash);
+    cudaFree(cb->cn64); cudaFree(cb->lc);
     cudaFree(cb->scratch); cudaFree(cb->stack_dbg);
     if (cb->host_ctx) nat_host_ctx_destroy(cb->host_ctx);
     delete cb->host_mutex;
@@ -461,7 +474,7 @@ static int launch_fused_stack(const StackLaunch& sl, cudaStream_t st) {
     stack::StackArgs sa;
     memset(&sa, 0, sizeof sa);
     stack::StackRef& r = sa.s;
-    r.cbf = cb->cbf; r.cn64 = cb->cn64; r.cn32 = cb->cn32; r.lc = cb->lc;
+    r.cbf = cb->cbf; r.cn64 = cb->cn64; r.cn32 = cb->cn32m; r.lc = cb->lc;
     r.r0 = sl.r0; r.rowinfo0 = sl.rowinfo0; r.rowamax0 = sl.rowamax0;
     r.r = sl.r; r.a = sl.a; r.rowinfo = sl.rowinfo; r.rowamax = sl.rowamax;
     r.codes = sl.codes; r.codes_ld = sl.codes_ld; r.code_off = sl.code_off;
@@ -581,14 +594,14 @@ static int encode_chunk(const EncodeCall& c, const Workspace& ws, const CUtensor
             NAT_LAUNCH(1, st, gemm::rvq_gemm_topk_kernel<true><<<std::min(n_tiles * n_chunks, cb->sm_count), gemm::NUM_THREADS,
                                                               gemm::SMEM_BYTES, st>>>(
                 map_a, cb->map_b, n, n_tiles, n_chunks, cb->dp / gemm::BLOCK_K, l * cb->kp, n_chunks, ws.rowinfo,
-                cb->cn32 + static_cast<long long>(l) * cb->kp, ws.cand, c.scores, cb->kp));
+                cb->cn32m + static_cast<long long>(l) * cb->kp, ws.cand, c.scores, cb->kp));
             NAT_LAUNCH(2, st, rows::argmin_from_acc_kernel<<<std::min((n + 7) / 8, cb->sm_count * 16), 256, 0, st>>>(
-                ua, c.scores, cb->kp, cb->cn32 + static_cast<long long>(l) * cb->kp));
+                ua, c.scores, cb->kp, cb->cn32m + static_cast<long long>(l) * cb->kp));
         } else if (!c.exact && c.temperatures == nullptr) {
             NAT_LAUNCH(1, st, gemm::rvq_gemm_topk_kernel<false><<<std::min(n_tiles, cb->sm_count), gemm::NUM_THREADS,
                                                                    gemm::SMEM_BYTES, st>>>(
                 map_a, cb->map_b, n, n_tiles, cb->kp / gemm::BLOCK_N, cb->dp / gemm::BLOCK_K, l * cb->kp, 1, ws.rowinfo,
-                cb->cn32 + static_cast<long long>(l) * cb->kp, ws.cand, nullptr, 0));
+                cb->cn32m + static_cast<long long>(l) * cb->kp, ws.cand, nullptr, 0));
             NAT_LAUNCH(2, st, rows::decide_update_kernel<<<std::min((n + 7) / 8, cb->sm_count * 16), 256, 0, st>>>(
                 ua, ws.cand, ws.scan_list, ws.scan_count + l));
             NAT_LAUNCH(3, st, rows::full_scan_kernel<<<scan_grid, rows::kScanThreads, scan_smem, st>>>(

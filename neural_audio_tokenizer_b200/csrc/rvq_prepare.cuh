@@ -68,6 +68,61 @@ convert_norms_kernel(const float* __restrict__ cbf, int K, int kp, int dp, __hal
     }
 }
 
+// Exact duplicates. A code vector equal to an EARLIER one of its layer can never be the answer (ties go to the lowest
+// index, nat.py:2157), but it sits inside every window its twin sits in: a codebook whose dead EMA entries have all
+// collapsed onto the same vector (nat.py:2205-2221 divides a decayed-to-zero sum by a decayed-to-zero count) would hand
+// dozens of candidates per frame to the exact re-rank, or send the frame to the exact scan. The argmin paths therefore
+// read `cn32m`, a copy of ||c||^2 in which every later duplicate is +inf like a padding code; the sampling path keeps
+// `cn32` (a duplicate has its own probability mass under multinomial).
+__global__ void __launch_bounds__(256)
+row_hash_kernel(const float* __restrict__ cbf, int K, int dp, unsigned long long* __restrict__ hash) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < K; k += warps) {
+        const float* c = cbf + static_cast<long long>(k) * dp;
+        unsigned long long h = 0x9E3779B97F4A7C15ull * (lane + 1);
+        for (int i = lane; i < dp; i += 32) {
+            unsigned int b = __float_as_uint(c[i]);
+            if (b == 0x80000000u) b = 0u;                            // -0 == +0
+            h = (h ^ b) * 0x100000001B3ull;
+            h ^= h >> 29;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o) * 0xD6E8FEB86659FD93ull;
+        h = __shfl_sync(0xffffffffu, h, 0);
+        if (lane == 0) hash[k] = h;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+mask_duplicates_kernel(const float* __restrict__ cbf, const unsigned long long* __restrict__ hash,
+                       const float* __restrict__ cn32, float* __restrict__ cn32m, int K, int kp, int dp) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < kp; k += warps) {
+        float out = cn32[k];
+        if (k < K) {
+            const unsigned long long hk = hash[k];
+            const float* ck = cbf + static_cast<long long>(k) * dp;
+            bool dup = false;
+            for (int j0 = 0; j0 < k && !dup; j0 += 32) {
+                const int j = j0 + lane;
+                unsigned hit = __ballot_sync(0xffffffffu, j < k && hash[j] == hk);
+                while (hit != 0 && !dup) {                          // hashes agree: compare the vectors themselves
+                    const int jj = j0 + __ffs(hit) - 1;
+                    hit &= hit - 1;
+                    const float* cj = cbf + static_cast<long long>(jj) * dp;
+                    bool same = true;
+                    for (int i = lane; i < dp; i += 32) same = same && (ck[i] == cj[i]);
+                    dup = __all_sync(0xffffffffu, same);
+                }
+            }
+            if (dup) out = __int_as_float(0x7F800000);
+        }
+        if (lane == 0) cn32m[k] = out;
+    }
+}
+
 __global__ void finish_consts_kernel(const int* __restrict__ scratch, int L, rows::LayerConst* __restrict__ lc) {
     const int l = threadIdx.x;
     if (l >= L) return;

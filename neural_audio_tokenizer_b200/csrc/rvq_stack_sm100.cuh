@@ -172,7 +172,7 @@ __device__ __forceinline__ void wait_counter(const unsigned* smem_counter, unsig
     const long long t0 = clock64();
     while (ld_acquire(smem_counter) < need) {
         __nanosleep(32);
-        if (clock64() - t0 > 4000000000LL) {
+        if (clock64() - t0 > 60000000000LL) {
             printf("nat_b200: update counter wait timed out (block %d, need %u, have %u)\n", blockIdx.x, need,
                    ld_acquire(smem_counter));
             __trap();

@@ -164,19 +164,18 @@ def _native_sample(pack: _CodebookPack, codebooks: Sequence[torch.Tensor], x_bct
     loss = torch.empty(L, dtype=torch.float32, device=dev) if want_loss else None
     noise = None
     if mode == "host_noise":
-        n_sampling = sum(1 for t in temperatures if t > 0)
-        if N * K * 4 * n_sampling > MAX_HOST_NOISE_BYTES:
+        # the device array is indexed by layer ([L, N, K], argmin layers' slices stay unused): that is what is allocated
+        if N * K * 4 * L > MAX_HOST_NOISE_BYTES:
             raise RuntimeError(
-                f"sampling_mode='host_noise' would ship {N * K * 4 * n_sampling / 2**30:.1f} GiB of host-drawn noise "
-                f"({N} frames x {K} codes x {n_sampling} layers); use sampling_mode='philox' (distributional parity) "
+                f"sampling_mode='host_noise' would ship {N * K * 4 * L / 2**30:.1f} GiB of host-drawn noise "
+                f"({N} frames x {K} codes x {L} layers); use sampling_mode='philox' (distributional parity) "
                 "or use_stochastic=False")
         # one draw per sampling layer, in layer order, exactly as torch.multinomial makes it on the CPU
         # (`at::empty_like(probs).exponential_(1)`); argmin layers consume nothing
-        host = torch.zeros((L, N, K), dtype=torch.float32, pin_memory=N * K > 0)
+        noise = torch.empty((L, N, K), dtype=torch.float32, device=dev)
         for l, t in enumerate(temperatures):
-            if t > 0:
-                host[l].copy_(torch.empty((N, K), dtype=torch.float32).exponential_(1))
-        noise = host.to(dev, non_blocking=True)
+            if t > 0 and N * K > 0:
+                noise[l].copy_(torch.empty((N, K), dtype=torch.float32).exponential_(1))
     elif mode not in ("philox", "philox_exact"):
         raise ValueError(f"unknown sampling_mode {mode!r}")
     if N == 0:

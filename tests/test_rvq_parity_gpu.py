@@ -259,6 +259,29 @@ def test_training_forward_samples_and_updates_ema_like_the_reference():
         assert torch.allclose(ql.ema_weight.cpu(), wgt[l], rtol=1e-5, atol=1e-5)
 
 
+def test_collapsed_codebook_entries_do_not_flood_the_rerank():
+    """Dead EMA entries collapse onto one vector (nat.py:2205-2221 divides a sum that decayed to zero by a count that
+    decayed to zero): hundreds of exact duplicates. Ties go to the lowest index, so later duplicates are masked out of
+    the coarse pass: indices still equal the reference's, and no frame falls back to the exact scan."""
+    from neural_audio_tokenizer_b200 import _lib
+    torch.manual_seed(13)
+    D, K, L, N = 128, 512, 3, 4000
+    cbs = torch.randn(L, K, D)
+    dead = torch.randperm(K)[:300]
+    cbs[:, dead] = 0.0                                                 # 300 collapsed entries per layer
+    cbs[1, dead[:5]] = -0.0                                            # -0 == +0: still duplicates
+    x = torch.randn(1, D, N) * 0.05                                    # frames near the origin: the zero code wins often
+    rvq = _dropin(cbs, collect_stats=True)
+    got = torch.stack(rvq.encode(x.cuda())).cpu().numpy()
+    ref = np.stack([c.numpy() for c in rvq_oracle.rvq_forward(x, list(cbs))[1]])
+    _check_codes(x, cbs, ref, got)
+    assert (got == int(dead.min())).any()                              # the collapsed vector is chosen, by its lowest index
+    st = rvq.last_stats.cpu().numpy()
+    assert st[:, _lib.STAT_FIELDS - 2].sum() == 0, st                  # NAT_STAT_FULL_SCAN: nobody scanned all K codes
+    rvq.exact_scan = True                                              # the exact path (no masking there) agrees
+    np.testing.assert_array_equal(torch.stack(rvq.encode(x.cuda())).cpu().numpy(), got)
+
+
 def test_errors_and_modes():
     from neural_audio_tokenizer_b200 import ResidualVectorQuantizer
     rvq = ResidualVectorQuantizer(32, 64, 2).cuda().eval()           # reference default: use_stochastic=True
