@@ -121,6 +121,7 @@ long long chunk_cap_rows() {
 
 struct Workspace {
     float* r;
+    float* r_work;        // a second set of residual rows: lets the fused kernel leave `r` (the prepared x rows) intact
     __half* a;
     float4* rowinfo;
     float* rowamax;
@@ -135,11 +136,11 @@ struct Workspace {
 constexpr size_t kWsFixed = 4096;
 constexpr int kMaxStacks = 2;             // S0-S3 and A0-A3 of one tokenizer per call
 
-size_t ws_per_row(int dp, int L) { return static_cast<size_t>(dp) * 6 + 16 + 4 + sizeof(nat::gemm::Cand) + 8 * L + 4; }
+size_t ws_per_row(int dp, int L) { return static_cast<size_t>(dp) * 10 + 16 + 4 + sizeof(nat::gemm::Cand) + 8 * L + 4; }
 
 bool carve(void* base, size_t bytes, int dp, int L, long long want_rows, Workspace* ws) {
-    if (bytes <= kWsFixed + 256 * 9) return false;
-    long long rows = static_cast<long long>((bytes - kWsFixed - 256 * 9) / ws_per_row(dp, L));
+    if (bytes <= kWsFixed + 256 * 10) return false;
+    long long rows = static_cast<long long>((bytes - kWsFixed - 256 * 10) / ws_per_row(dp, L));
     rows = std::min(rows, round_up(want_rows, 128));
     rows = rows / 128 * 128;
     if (rows < 128) return false;
@@ -148,6 +149,7 @@ bool carve(void* base, size_t bytes, int dp, int L, long long want_rows, Workspa
     ws->scan_count = reinterpret_cast<int*>(take(kWsFixed / 2));
     ws->loss_acc = reinterpret_cast<double*>(take(kWsFixed / 2));
     ws->r = reinterpret_cast<float*>(take(static_cast<size_t>(rows) * dp * 4));
+    ws->r_work = reinterpret_cast<float*>(take(static_cast<size_t>(rows) * dp * 4));
     ws->a = reinterpret_cast<__half*>(take(static_cast<size_t>(rows) * dp * 2));
     ws->rowinfo = reinterpret_cast<float4*>(take(static_cast<size_t>(rows) * 16));
     ws->rowamax = reinterpret_cast<float*>(take(static_cast<size_t>(rows) * 4));
@@ -398,10 +400,10 @@ static size_t small_input_scores_bytes(const nat_rvq_codebooks* cb, long long n_
 }
 
 size_t nat_rvq_workspace_bytes(const nat_rvq_codebooks* cb, int64_t n_frames) {
-    if (cb == nullptr || n_frames <= 0) return kWsFixed + 256 * 9 + 128 * ws_per_row(64, 16);
+    if (cb == nullptr || n_frames <= 0) return kWsFixed + 256 * 10 + 128 * ws_per_row(64, 16);
     // two lanes, each holding half of the frames rounded up to a tile (see nat_rvq_encode_f32)
     const long long per_lane = std::min<long long>(round_up((n_frames + 1) / 2, 128), chunk_cap_rows() / 2);
-    const size_t lane_bytes = static_cast<size_t>(round_up(kWsFixed + 256 * 9 + per_lane * ws_per_row(cb->dp, cb->L), 256));
+    const size_t lane_bytes = static_cast<size_t>(round_up(kWsFixed + 256 * 10 + per_lane * ws_per_row(cb->dp, cb->L), 256));
     return 2 * lane_bytes + small_input_scores_bytes(cb, n_frames);
 }
 
@@ -543,19 +545,39 @@ static int encode_chunk(const EncodeCall& c, const Workspace& ws, const CUtensor
         // one persistent launch for all L layers (rvq_stack_sm100.cuh); the update warps write in place
         StackLaunch sl;
         sl.cb = cb;
+        // Codes only: the update warps work in place. With the quantised sum or the losses asked for (the form
+        // ResidualVectorQuantizer.forward returns, nat.py:1410-1415) the kernel still runs its codes-only form, but
+        // writes its residuals to the second set of rows: the prepared x rows stay intact and ONE replay of the chain
+        // from the emitted codes (bit-identical op order) yields the quantised sum and every layer's loss sums.
+        const bool extras = c.want_loss || c.quantized != nullptr;
         sl.r0 = ws.r; sl.rowinfo0 = ws.rowinfo; sl.rowamax0 = ws.rowamax;
-        sl.r = ws.r; sl.a = ws.a; sl.rowinfo = ws.rowinfo; sl.rowamax = ws.rowamax;
+        sl.r = extras ? ws.r_work : ws.r; sl.a = ws.a; sl.rowinfo = ws.rowinfo; sl.rowamax = ws.rowamax;
         sl.codes = c.codes; sl.codes_ld = c.N; sl.code_off = n0;
-        sl.row_loss = c.want_loss ? ws.row_loss : nullptr; sl.loss_ld = ws.rows;
         sl.stats = c.stats;
         sl.map_a0 = map_a; sl.map_a = map_a;
         sl.n_rows = n; sl.code_dtype = c.code_dtype;
         if (int rc = launch_fused_stack(sl, st)) return rc;
-        if (c.want_loss)
-            for (int l = 0; l < cb->L; ++l)
-                NAT_LAUNCH(4, st, rows::reduce_loss_kernel<<<1, 1024, 0, st>>>(ws.row_loss + static_cast<long long>(l) * ws.rows,
-                                                                              n, ws.loss_acc + l));
+        if (extras) {
+            const int warps_grid = std::min((n + 7) / 8, cb->sm_count * 16);
+            NAT_LAUNCH(5, st, rows::reconstruct_rows_kernel<<<warps_grid, 256, 0, st>>>(
+                ws.r, c.quantized != nullptr ? ws.r_work : nullptr, n, cb->dp, cb->cbf, cb_layer_ld, cb->L, c.codes,
+                c.code_dtype, c.N, n0, c.want_loss ? ws.row_loss : nullptr, ws.rows));
+            if (c.want_loss)
+                for (int l = 0; l < cb->L; ++l)
+                    NAT_LAUNCH(4, st, rows::reduce_loss_kernel<<<1, 1024, 0, st>>>(ws.row_loss + static_cast<long long>(l) * ws.rows,
+                                                                                  n, ws.loss_acc + l));
+            if (c.quantized != nullptr) {
+                if (c.layout == NAT_LAYOUT_ROWS) {
+                    NAT_LAUNCH(5, st, rows::copy_rows_out_kernel<<<cb->sm_count * 8, 256, 0, st>>>(ws.r_work, n, cb->dp, cb->D,
+                                                                                                c.quantized + n0 * cb->D));
+                } else {
+                    dim3 grid((n + 31) / 32, (cb->D + 31) / 32);
+                    NAT_LAUNCH(5, st, rows::rows_to_bct_kernel<<<grid, 256, 0, st>>>(ws.r_work, cb->dp, c.T, cb->D, n0, n, c.quantized));
+                }
+            }
+        }
         NAT_CUDA(cudaGetLastError());
+        return NAT_OK;
     } else
     for (int l = 0; l < cb->L; ++l) {
         rows::UpdateArgs ua;
@@ -623,7 +645,7 @@ static int encode_chunk(const EncodeCall& c, const Workspace& ws, const CUtensor
             dim3 grid((n + 31) / 32, cb->dp / 32);
             NAT_LAUNCH(0, st, rows::bct_to_rows_kernel<<<grid, 256, 0, st>>>(c.x, c.T, cb->D, n0, n, cb->dp, ws.r));
         }
-        NAT_LAUNCH(5, st, rows::reconstruct_rows_kernel<<<warps_grid, 256, 0, st>>>(ws.r, n, cb->dp, cb->cbf, cb_layer_ld,
+        NAT_LAUNCH(5, st, rows::reconstruct_rows_kernel<<<warps_grid, 256, 0, st>>>(ws.r, ws.r, n, cb->dp, cb->cbf, cb_layer_ld,
                                                                                  cb->L, c.codes, c.code_dtype, c.N, n0));
         if (c.layout == NAT_LAYOUT_ROWS) {
             NAT_LAUNCH(5, st, rows::copy_rows_out_kernel<<<cb->sm_count * 8, 256, 0, st>>>(ws.r, n, cb->dp, cb->D,
@@ -672,7 +694,7 @@ static int encode_impl(const nat_rvq_codebooks* cb_const, const float* x_dev, in
     size_t scores_bytes = (temperatures == nullptr && !(flags & NAT_RVQ_EXACT_SCAN) && small_path_enabled() && !two)
                               ? small_input_scores_bytes(cb, N) : 0;
     if (scores_bytes != 0) {
-        const size_t main_bytes = static_cast<size_t>(round_up(kWsFixed + 256 * 9 + round_up(N, 128) * ws_per_row(cb->dp, cb->L), 256));
+        const size_t main_bytes = static_cast<size_t>(round_up(kWsFixed + 256 * 10 + round_up(N, 128) * ws_per_row(cb->dp, cb->L), 256));
         if (workspace_bytes < main_bytes + scores_bytes + 256) scores_bytes = 0;
         else workspace_bytes = (workspace_bytes - scores_bytes) & ~static_cast<size_t>(255);
     }

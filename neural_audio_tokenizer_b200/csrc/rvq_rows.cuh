@@ -770,31 +770,44 @@ __global__ void finish_loss_kernel(const double* __restrict__ acc, const double*
 }
 
 // ---------------------------------------------------------------------------------------------------- outputs
-// rows [n, Dp] holding x -> rows holding sum_l q_ste_l, replaying the chain from the emitted codes. One warp/frame.
+// rows [n, Dp] holding x -> rows holding sum_l q_ste_l, replaying the chain from the emitted codes; optionally the
+// per-frame loss sums of every layer (sum_d t^2 with t = q - r, nat.py:2162-2163) from the same replay. One warp/frame.
+// `src` may equal `dst` (in place); `dst` may be null (losses only).
 __global__ void __launch_bounds__(256)
-reconstruct_rows_kernel(float* __restrict__ r, int n, int dp, const float* __restrict__ cb_all, long long cb_layer_ld,
-                        int L, const void* __restrict__ codes, int code_dtype, long long codes_ld,
-                        long long code_off) {
+reconstruct_rows_kernel(const float* __restrict__ src, float* dst, int n, int dp, const float* __restrict__ cb_all,
+                        long long cb_layer_ld, int L, const void* __restrict__ codes, int code_dtype,
+                        long long codes_ld, long long code_off, double* __restrict__ row_loss = nullptr,
+                        long long loss_ld = 0) {
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     const int dp4 = dp >> 2;
     for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
-        float4* r4 = reinterpret_cast<float4*>(r + static_cast<long long>(row) * dp);
+        const float4* s4 = reinterpret_cast<const float4*>(src + static_cast<long long>(row) * dp);
+        float4* d4 = dst != nullptr ? reinterpret_cast<float4*>(dst + static_cast<long long>(row) * dp) : nullptr;
         int js[16];
-        for (int l = 0; l < L; ++l) js[l] = load_code(codes, code_dtype, l * codes_ld + code_off + row);
+        double loss[16];
+        for (int l = 0; l < L; ++l) { js[l] = load_code(codes, code_dtype, l * codes_ld + code_off + row); loss[l] = 0.0; }
         for (int i = lane; i < dp4; i += 32) {
-            float4 rv = r4[i];
+            float4 rv = s4[i];
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int l = 0; l < L; ++l) {
                 const float4 cv = __ldg(reinterpret_cast<const float4*>(cb_all + l * cb_layer_ld +
                                                                          static_cast<long long>(js[l]) * dp) + i);
                 float t, q;
-                t = __fsub_rn(cv.x, rv.x); q = __fadd_rn(rv.x, t); rv.x = __fsub_rn(rv.x, q); acc.x = l ? __fadd_rn(acc.x, q) : q;
-                t = __fsub_rn(cv.y, rv.y); q = __fadd_rn(rv.y, t); rv.y = __fsub_rn(rv.y, q); acc.y = l ? __fadd_rn(acc.y, q) : q;
-                t = __fsub_rn(cv.z, rv.z); q = __fadd_rn(rv.z, t); rv.z = __fsub_rn(rv.z, q); acc.z = l ? __fadd_rn(acc.z, q) : q;
-                t = __fsub_rn(cv.w, rv.w); q = __fadd_rn(rv.w, t); rv.w = __fsub_rn(rv.w, q); acc.w = l ? __fadd_rn(acc.w, q) : q;
+                double ls = 0.0;
+                t = __fsub_rn(cv.x, rv.x); q = __fadd_rn(rv.x, t); rv.x = __fsub_rn(rv.x, q); acc.x = l ? __fadd_rn(acc.x, q) : q; ls += static_cast<double>(__fmul_rn(t, t));
+                t = __fsub_rn(cv.y, rv.y); q = __fadd_rn(rv.y, t); rv.y = __fsub_rn(rv.y, q); acc.y = l ? __fadd_rn(acc.y, q) : q; ls += static_cast<double>(__fmul_rn(t, t));
+                t = __fsub_rn(cv.z, rv.z); q = __fadd_rn(rv.z, t); rv.z = __fsub_rn(rv.z, q); acc.z = l ? __fadd_rn(acc.z, q) : q; ls += static_cast<double>(__fmul_rn(t, t));
+                t = __fsub_rn(cv.w, rv.w); q = __fadd_rn(rv.w, t); rv.w = __fsub_rn(rv.w, q); acc.w = l ? __fadd_rn(acc.w, q) : q; ls += static_cast<double>(__fmul_rn(t, t));
+                if (row_loss != nullptr) loss[l] += ls;
             }
-            r4[i] = acc;
+            if (d4 != nullptr) d4[i] = acc;
+        }
+        if (row_loss != nullptr) {
+            for (int l = 0; l < L; ++l) {
+                const double v = warp_sum(loss[l]);
+                if (lane == 0) row_loss[l * loss_ld + row] = v;
+            }
         }
     }
 }
