@@ -168,6 +168,17 @@ size_t nat_rvq_stacks_workspace_bytes(const nat_rvq_codebooks* const* stacks, in
 int nat_rvq_encode_stacks_f32(const nat_rvq_codebooks* const* stacks, int n_stacks, const float* const* x_dev,
                               int layout, int64_t B, int64_t T, void* codes_out_dev, int code_dtype,
                               void* workspace_dev, size_t workspace_bytes, int flags, void* stream);
+/* 1 when the stacks take the shared-preparation + persistent-kernel form for this many frames. */
+int nat_rvq_stacks_fused(const nat_rvq_codebooks* const* stacks, int n_stacks, int64_t n_frames);
+/* The same with the reference's time-base alignment folded into the preparation's loads. Replaces
+ * `F.interpolate(features, size=T_target, mode='linear', align_corners=False)` at nat.py:3225-3236 followed by the two
+ * quantiser calls: x_dev[i] is [B, D, t_in[i]] (time fastest), every stack is quantised on the common T-frame time
+ * base (the caller passes T = min_i t_in[i], nat.py:3227), with the floating-point steps of ATen's CPU kernel
+ * (bit-identical to the reference's CPU call). Only where nat_rvq_stacks_fused() is 1; elsewhere NAT_ERR_UNSUPPORTED
+ * (align with nat_interp_linear_f32 first). */
+int nat_rvq_encode_stacks_aligned_f32(const nat_rvq_codebooks* const* stacks, int n_stacks, const float* const* x_dev,
+                                      const int64_t* t_in, int64_t B, int64_t T, void* codes_out_dev, int code_dtype,
+                                      void* workspace_dev, size_t workspace_bytes, int flags, void* stream);
 /* Same call, timed per kernel class like nat_rvq_encode_profile_f32 (bench.py's roofline leg). */
 int nat_rvq_encode_stacks_profile_f32(const nat_rvq_codebooks* const* stacks, int n_stacks, const float* const* x_dev,
                                       int layout, int64_t B, int64_t T, void* codes_out_dev, int code_dtype,

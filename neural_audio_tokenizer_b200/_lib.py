@@ -43,6 +43,9 @@ _SIGNATURES = [
     ("nat_rvq_stacks_workspace_bytes", c_size_t, [POINTER(c_void_p), c_int, c_int64]),
     ("nat_rvq_encode_stacks_f32", c_int, [POINTER(c_void_p), c_int, POINTER(c_void_p), c_int, c_int64, c_int64, c_void_p,
                                           c_int, c_void_p, c_size_t, c_int, c_void_p]),
+    ("nat_rvq_stacks_fused", c_int, [POINTER(c_void_p), c_int, c_int64]),
+    ("nat_rvq_encode_stacks_aligned_f32", c_int, [POINTER(c_void_p), c_int, POINTER(c_void_p), POINTER(c_int64), c_int64,
+                                                  c_int64, c_void_p, c_int, c_void_p, c_size_t, c_int, c_void_p]),
     ("nat_rvq_encode_stacks_profile_f32", c_int, [POINTER(c_void_p), c_int, POINTER(c_void_p), c_int, c_int64, c_int64,
                                                   c_void_p, c_int, c_void_p, c_size_t, c_int, c_void_p,
                                                   POINTER(c_float)]),

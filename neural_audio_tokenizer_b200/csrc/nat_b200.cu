@@ -412,8 +412,18 @@ size_t nat_rvq_workspace_bytes(const nat_rvq_codebooks* cb, int64_t n_frames) {
 // frame. `rowinfo_b` / `lc_b`: a second stack quantising the same frames gets its own window from the same sums.
 static int launch_layer0_prep(const nat_rvq_codebooks* cb, const Workspace& ws, const float* x, int layout,
                               long long T, long long n0, int n, cudaStream_t st, float4* rowinfo_b = nullptr,
-                              const nat::rows::LayerConst* lc_b = nullptr) {
+                              const nat::rows::LayerConst* lc_b = nullptr, long long T_in = 0) {
     using namespace nat;
+    if (T_in > 0) {          // time-base alignment fused into the loads: [B, D, T_in] -> T frames
+        const size_t smem = static_cast<size_t>(rows::kPrepFrames) * (cb->dp + 1) * sizeof(float);
+        if (layout != NAT_LAYOUT_BCT || smem > 200 * 1024)
+            return fail(NAT_ERR_UNSUPPORTED, "time-base alignment is fused into the [B, D, T] preparation only");
+        const float scale = static_cast<float>(T_in) / static_cast<float>(T);      // area_pixel_compute_scale<float>
+        NAT_LAUNCH(0, st, rows::prep_bct_fused_kernel<<<(n + rows::kPrepFrames - 1) / rows::kPrepFrames, rows::kPrepThreads, smem, st>>>(
+            x, T, cb->D, n0, n, cb->dp, ws.r, ws.a, ws.rowinfo, ws.rowamax, cb->lc, rowinfo_b, lc_b, T_in, scale));
+        NAT_CUDA(cudaGetLastError());
+        return NAT_OK;
+    }
     const int warps_grid = std::min((n + 7) / 8, cb->sm_count * 16);
     if (layout == NAT_LAYOUT_ROWS) {
         NAT_LAUNCH(0, st, rows::prep_rows_kernel<<<warps_grid, 256, 0, st>>>(x + n0 * cb->D, cb->D, n, cb->D, cb->dp, ws.r, ws.a,
@@ -1025,8 +1035,35 @@ size_t nat_rvq_stacks_workspace_bytes(const nat_rvq_codebooks* const* stacks, in
     return need;
 }
 
+int nat_rvq_stacks_fused(const nat_rvq_codebooks* const* stacks, int n_stacks, int64_t n_frames) {
+    if (stacks == nullptr || n_stacks < 1) return 0;
+    for (int i = 0; i < n_stacks; ++i) if (stacks[i] == nullptr) return 0;
+    return stacks_fusable(stacks, n_stacks, n_frames) ? 1 : 0;
+}
+
+static int encode_stacks_impl(const nat_rvq_codebooks* const* stacks, int n_stacks, const float* const* x_dev,
+                              const int64_t* t_in, int layout, int64_t B, int64_t T, void* codes_out_dev, int code_dtype,
+                              void* workspace_dev, size_t workspace_bytes, int flags, void* stream);
+
 int nat_rvq_encode_stacks_f32(const nat_rvq_codebooks* const* stacks, int n_stacks, const float* const* x_dev,
                               int layout, int64_t B, int64_t T, void* codes_out_dev, int code_dtype,
+                              void* workspace_dev, size_t workspace_bytes, int flags, void* stream) {
+    return encode_stacks_impl(stacks, n_stacks, x_dev, nullptr, layout, B, T, codes_out_dev, code_dtype, workspace_dev,
+                              workspace_bytes, flags, stream);
+}
+
+int nat_rvq_encode_stacks_aligned_f32(const nat_rvq_codebooks* const* stacks, int n_stacks, const float* const* x_dev,
+                                      const int64_t* t_in, int64_t B, int64_t T, void* codes_out_dev, int code_dtype,
+                                      void* workspace_dev, size_t workspace_bytes, int flags, void* stream) {
+    if (t_in == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null time extents");
+    for (int i = 0; i < n_stacks; ++i)
+        if (t_in[i] < 1 || t_in[i] > 0x7FFFFFFF || T > 0x7FFFFFFF) return fail(NAT_ERR_INVALID_ARGUMENT, "bad time extent");
+    return encode_stacks_impl(stacks, n_stacks, x_dev, t_in, NAT_LAYOUT_BCT, B, T, codes_out_dev, code_dtype, workspace_dev,
+                              workspace_bytes, flags, stream);
+}
+
+static int encode_stacks_impl(const nat_rvq_codebooks* const* stacks, int n_stacks, const float* const* x_dev,
+                              const int64_t* t_in, int layout, int64_t B, int64_t T, void* codes_out_dev, int code_dtype,
                               void* workspace_dev, size_t workspace_bytes, int flags, void* stream) {
     using namespace nat;
     if (stacks == nullptr || x_dev == nullptr || n_stacks < 1) return fail(NAT_ERR_INVALID_ARGUMENT, "null argument");
@@ -1040,6 +1077,11 @@ int nat_rvq_encode_stacks_f32(const nat_rvq_codebooks* const* stacks, int n_stac
     if (codes_out_dev == nullptr || workspace_dev == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null device pointer");
     const int cbytes = code_bytes(code_dtype);
     if (!stacks_fusable(stacks, n_stacks, N) || (flags & NAT_RVQ_EXACT_SCAN)) {
+        if (t_in != nullptr)
+            for (int i = 0; i < n_stacks; ++i)
+                if (t_in[i] != T)
+                    return fail(NAT_ERR_UNSUPPORTED, "time-base alignment is fused into the two-stack preparation only "
+                                "(nat_rvq_stacks_fused() says when); align with nat_interp_linear_f32 first");
         long long layer0 = 0;
         for (int i = 0; i < n_stacks; ++i) {
             if (int rc = nat_rvq_encode_f32(stacks[i], x_dev[i], layout, B, T, static_cast<char*>(codes_out_dev) + layer0 * N * cbytes,
@@ -1055,7 +1097,8 @@ int nat_rvq_encode_stacks_f32(const nat_rvq_codebooks* const* stacks, int n_stac
     NAT_CUDA(cudaGetDevice(&dev));
     if (dev != s0->device) return fail(NAT_ERR_INVALID_ARGUMENT, "codebooks live on device %d, current device is %d", s0->device, dev);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int n_inputs = x_dev[0] == x_dev[1] ? 1 : 2;
+    const long long tin0 = (t_in != nullptr && t_in[0] != T) ? t_in[0] : 0, tin1 = (t_in != nullptr && t_in[1] != T) ? t_in[1] : 0;
+    const int n_inputs = (x_dev[0] == x_dev[1] && tin0 == tin1) ? 1 : 2;
     MultiWs ws;
     if (!carve_multi(workspace_dev, workspace_bytes, s0->dp, n_inputs, std::min<long long>(N, chunk_cap_rows()), &ws))
         return fail(NAT_ERR_WORKSPACE, "workspace of %zu bytes cannot hold one 128-frame tile (need %zu)", workspace_bytes,
@@ -1076,12 +1119,12 @@ int nat_rvq_encode_stacks_f32(const nat_rvq_codebooks* const* stacks, int n_stac
         memset(&w0, 0, sizeof w0);
         w0.r = ws.r_prep[0]; w0.a = ws.a_prep[0]; w0.rowinfo = ws.rowinfo[0]; w0.rowamax = ws.rowamax[0]; w0.rows = ws.rows;
         if (n_inputs == 1) {
-            if (int rc = launch_layer0_prep(s0, w0, x_dev[0], layout, T, n0, n, st, ws.rowinfo[1], s1->lc)) return rc;
+            if (int rc = launch_layer0_prep(s0, w0, x_dev[0], layout, T, n0, n, st, ws.rowinfo[1], s1->lc, tin0)) return rc;
         } else {
-            if (int rc = launch_layer0_prep(s0, w0, x_dev[0], layout, T, n0, n, st)) return rc;
+            if (int rc = launch_layer0_prep(s0, w0, x_dev[0], layout, T, n0, n, st, nullptr, nullptr, tin0)) return rc;
             Workspace w1 = w0;
             w1.r = ws.r_prep[1]; w1.a = ws.a_prep[1]; w1.rowinfo = ws.rowinfo[1]; w1.rowamax = ws.rowamax[1];
-            if (int rc = launch_layer0_prep(s1, w1, x_dev[1], layout, T, n0, n, st)) return rc;
+            if (int rc = launch_layer0_prep(s1, w1, x_dev[1], layout, T, n0, n, st, nullptr, nullptr, tin1)) return rc;
         }
         for (int i = 0; i < 2; ++i) {
             StackLaunch sl;

@@ -153,17 +153,33 @@ __global__ void __launch_bounds__(kPrepThreads)
 prep_bct_fused_kernel(const float* __restrict__ x, long long T, int D, long long n0, int n, int dp,
                       float* __restrict__ r, __half* __restrict__ a, float4* __restrict__ rowinfo,
                       float* __restrict__ rowamax, const LayerConst* __restrict__ lc,
-                      float4* __restrict__ rowinfo_b = nullptr, const LayerConst* __restrict__ lc_b = nullptr) {
+                      float4* __restrict__ rowinfo_b = nullptr, const LayerConst* __restrict__ lc_b = nullptr,
+                      long long T_in = 0, float scale = 1.f) {
     extern __shared__ float s_tile[];                   // [32][dp + 1]
     constexpr int kWarps = kPrepThreads / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ld = dp + 1;
     const int f0 = blockIdx.x * kPrepFrames;
     const int f = f0 + lane;
-    long long src = -1;
+    // T_in > 0: x is [B, D, T_in] and frame t of the T-frame time base is the two-tap linear interpolation of
+    // F.interpolate(x, size=T, mode='linear', align_corners=False) (nat.py:3225-3236), in the floating-point steps of
+    // interp.cuh (bit-identical to the reference's CPU call): the alignment costs no pass of its own.
+    long long src = -1, src1 = -1, pitch = T;
+    float l0 = 1.f, l1 = 0.f;
     if (f < n) {
         const long long g = n0 + f, b = g / T, t = g - b * T;
-        src = b * D * T + t;
+        if (T_in > 0) {
+            const float real = fmaxf(__fmaf_rn(scale, static_cast<float>(static_cast<int>(t)) + 0.5f, -0.5f), 0.f);
+            const int i0 = min(static_cast<int>(real), static_cast<int>(T_in) - 1);
+            const int i1 = i0 + (i0 < T_in - 1 ? 1 : 0);
+            l1 = fminf(fmaxf(__fsub_rn(real, static_cast<float>(i0)), 0.f), 1.f);
+            l0 = __fsub_rn(1.f, l1);
+            src = b * D * T_in + i0;
+            src1 = b * D * T_in + i1;
+            pitch = T_in;
+        } else {
+            src = b * D * T + t;
+        }
     }
     // lane = frame (consecutive t: one 128-byte line per feature), warps stride over features, 16 loads in flight
     // per thread (the kernel is latency-bound otherwise: HBM needs ~30 KB in flight per SM)
@@ -173,7 +189,14 @@ prep_bct_fused_kernel(const float* __restrict__ x, long long T, int D, long long
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int d = d0 + u;
-            v[u] = (src >= 0 && d < D) ? __ldcs(x + src + static_cast<long long>(d) * T) : 0.f;
+            v[u] = (src >= 0 && d < D) ? __ldcs(x + src + static_cast<long long>(d) * pitch) : 0.f;
+        }
+        if (T_in > 0) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int d = d0 + u;
+                if (src >= 0 && d < D) v[u] = __fmaf_rn(l0, v[u], __fmul_rn(l1, __ldcs(x + src1 + static_cast<long long>(d) * pitch)));
+            }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)

@@ -45,7 +45,8 @@ def _handles(stacks):
 def encode_stacks(stacks: Sequence[ResidualVectorQuantizer], x: Union[torch.Tensor, Sequence[torch.Tensor]],
                   code_dtype: torch.dtype = torch.int16, out: Optional[torch.Tensor] = None,
                   workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """x: one [B, C, T] CUDA tensor for all stacks, or one per stack (same B, T). Returns [sum L, B, T] codes."""
+    """x: one [B, C, T] CUDA tensor for all stacks, or one per stack (same B; streams of different length are aligned
+    to the shortest one by linear interpolation first, as nat.py:3225-3236 does). Returns [sum L, B, T] codes."""
     lib = _lib.load()
     dev = _check_stacks(stacks)
     xs = [x] * len(stacks) if isinstance(x, torch.Tensor) else list(x)
@@ -63,10 +64,12 @@ def encode_stacks(stacks: Sequence[ResidualVectorQuantizer], x: Union[torch.Tens
         if t.dtype != torch.float32:
             raise TypeError(f"expected float32 features, got {t.dtype}")
         cont.append(t if t.is_contiguous() else t.contiguous())
-    B, _, T = cont[0].shape
+    B = cont[0].shape[0]
+    t_ins = [int(t.shape[2]) for t in cont]
+    T = min(t_ins)                                   # the common time base, nat.py:3227
     for t in cont:
-        if t.device != dev or (t.shape[0], t.shape[2]) != (B, T):
-            raise ValueError("inputs must share batch, time extent and the stacks' device")
+        if t.device != dev or t.shape[0] != B:
+            raise ValueError("inputs must share the batch extent and the stacks' device")
     L_total = sum(len(s.quantizers) for s in stacks)
     if out is None:
         out = torch.empty((L_total, B, T), dtype=code_dtype, device=dev)
@@ -78,10 +81,23 @@ def encode_stacks(stacks: Sequence[ResidualVectorQuantizer], x: Union[torch.Tens
         _, harr = _handles(stacks)
         need = lib.nat_rvq_stacks_workspace_bytes(harr, len(stacks), B * T)
         ws = workspace if workspace is not None and workspace.numel() >= need else torch.empty(need, dtype=torch.uint8, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        if any(t != T for t in t_ins):
+            # Streams of different length are brought to the shorter time base first (nat.py:3225-3236). Where the
+            # stacks take the shared-preparation form the interpolation is folded into the preparation's loads;
+            # elsewhere it is a kernel of its own. Either way the reference's CPU arithmetic, bit for bit.
+            if lib.nat_rvq_stacks_fused(harr, len(stacks), B * T):
+                xarr = (ctypes.c_void_p * len(cont))(*[t.data_ptr() for t in cont])
+                tarr = (ctypes.c_int64 * len(cont))(*t_ins)
+                _lib.check(lib.nat_rvq_encode_stacks_aligned_f32(harr, len(stacks), xarr, tarr, B, T, out.data_ptr(),
+                                                                 _CODE_DTYPES[code_dtype], ws.data_ptr(), ws.numel(), 0,
+                                                                 stream))
+                return out
+            from .align import interpolate_linear
+            cont = [t if t.shape[2] == T else interpolate_linear(t, T) for t in cont]
         xarr = (ctypes.c_void_p * len(cont))(*[t.data_ptr() for t in cont])
         _lib.check(lib.nat_rvq_encode_stacks_f32(harr, len(stacks), xarr, _lib.LAYOUT_BCT, B, T, out.data_ptr(),
-                                                 _CODE_DTYPES[code_dtype], ws.data_ptr(), ws.numel(), 0,
-                                                 torch.cuda.current_stream(dev).cuda_stream))
+                                                 _CODE_DTYPES[code_dtype], ws.data_ptr(), ws.numel(), 0, stream))
     return out
 
 

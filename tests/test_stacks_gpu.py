@@ -132,3 +132,23 @@ def test_host_contexts_on_two_threads_share_the_codebook_handles():
         t.join()
     assert not errs, errs
     assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+
+
+@pytest.mark.parametrize("T_sem,T_ac", [(9000, 7013), (6000, 6000), (300, 260)])
+def test_streams_of_different_length_are_aligned_like_the_reference(T_sem, T_ac):
+    """nat.py:3225-3236: the longer feature stream is brought to the shorter time base with
+    F.interpolate(mode='linear', align_corners=False) before both quantiser calls. Folded into the layer-0
+    preparation's loads where the stacks share a launch form, a kernel of its own elsewhere; in both cases the index
+    streams equal quantising torch's CPU interpolation (the reference's own arithmetic)."""
+    import torch.nn.functional as F
+    from neural_audio_tokenizer_b200 import encode_stacks
+    stacks = _stacks(256, 512, 4, 4, seed=21)
+    sem = torch.randn(1, 256, T_sem, generator=torch.Generator().manual_seed(1))
+    ac = torch.randn(1, 256, T_ac, generator=torch.Generator().manual_seed(2))
+    T = min(T_sem, T_ac)
+    ref_in = [t if t.shape[-1] == T else F.interpolate(t, size=T, mode="linear", align_corners=False) for t in (sem, ac)]
+    got = encode_stacks(stacks, [sem.cuda(), ac.cuda()], torch.int16)
+    assert got.shape == (8, 1, T)
+    want = torch.cat([torch.stack(s.encode(x.cuda())) for s, x in zip(stacks, ref_in)])     # quantise torch's CPU interpolation
+    assert torch.equal(got.long(), want)
+    _assert_matches_oracle(stacks, ref_in, got)
