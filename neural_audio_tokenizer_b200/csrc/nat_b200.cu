@@ -92,8 +92,18 @@ EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-// fp16 row-major [rows, cols] -> 2-D map with a (64 x box_rows) box and 128-byte swizzle.
+// fp16 row-major [rows, cols] -> 2-D map with a (64 x box_rows) box and 128-byte swizzle. The descriptor is a pure
+// function of its arguments: the last few are remembered per thread, so a caller that reuses its workspace (the 1 s
+// chunk path) does not re-encode the same operand map on every call.
 int make_map_f16(CUtensorMap* map, const void* base, long long rows, long long cols, int box_rows) {
+    struct Entry { const void* base; long long rows, cols; int box_rows; CUtensorMap map; };
+    thread_local Entry cache[8];
+    thread_local int next = 0, used = 0;
+    for (int i = 0; i < used; ++i)
+        if (cache[i].base == base && cache[i].rows == rows && cache[i].cols == cols && cache[i].box_rows == box_rows) {
+            *map = cache[i].map;
+            return NAT_OK;
+        }
     EncodeTiledFn fn = encode_tiled_fn();
     if (fn == nullptr) return fail(NAT_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
@@ -104,6 +114,9 @@ int make_map_f16(CUtensorMap* map, const void* base, long long rows, long long c
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(NAT_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    cache[next] = Entry{base, rows, cols, box_rows, *map};
+    next = (next + 1) % 8;
+    used = std::min(used + 1, 8);
     return NAT_OK;
 }
 
