@@ -42,9 +42,6 @@
 #ifndef NAT_UPD_WARPS
 #define NAT_UPD_WARPS 16
 #endif
-#ifndef NAT_REPLAY_FAST
-#define NAT_REPLAY_FAST 1        // replays in the update loop: code index prefetched per job, code vector loaded in one go
-#endif
 #ifndef NAT_REGS_EPI
 #define NAT_REGS_EPI 88
 #define NAT_REGS_UPD 88
@@ -742,10 +739,6 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a0,  // fp16 [rows, dp]
                     // again before use and cost a second DRAM read; measured 4.6 % slower. A late one, issued when the
                     // job's candidates arrive, measured 4.6 % slower than none as well.)
                     if (residual_needed && nrows > 0 && lane < nrows) am_old = __ldcg((l == 0 ? sk.rowamax0 : sk.rowamax) + row0 + lane);
-#if NAT_REPLAY_FAST
-                    int jrep1 = 0;                     // lane rr: the code row rr took one layer ago (written by this warp)
-                    if (n_replay >= 1 && lane < nrows) jrep1 = rows::load_code(codes_l, p.code_dtype, code_base - sk.codes_ld + row0 + lane);
-#endif
                     const uint32_t slot = job & 1;
                     const long long t0 = w_cfull.begin();
                     mbar_wait(&cfull[slot], (job >> 1) & 1);
@@ -845,25 +838,8 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a0,  // fp16 [rows, dp]
                                 else for (int e = 0; e < 8; ++e) cur[g].v[e] = 1.f;          // timing experiment only
 #pragma unroll 1
                             for (int back = n_replay; back > 0; --back) {
-#if NAT_REPLAY_FAST
-                                // the replayed code vector travels through cv (free until the new code's vector is
-                                // loaded below), all of it in flight at once; its index was fetched at the job's start
-                                const int jp = back == 1 ? __shfl_sync(0xffffffffu, jrep1, rr)
-                                                         : rows::load_code(codes_l, p.code_dtype, code_base - back * sk.codes_ld + row);
-                                const float* prow = cb_l + (static_cast<long long>(jp) - static_cast<long long>(back) * p.K) * p.dp;
-#pragma unroll
-                                for (int g = 0; g < NH; ++g) cv[g] = ldcg256(prow + (g * 32 + lane) * 8);
-#pragma unroll
-                                for (int g = 0; g < NH; ++g)
-#pragma unroll
-                                    for (int e = 0; e < 8; ++e) {
-                                        const float t = __fsub_rn(cv[g].v[e], cur[g].v[e]);
-                                        cur[g].v[e] = __fsub_rn(cur[g].v[e], __fadd_rn(cur[g].v[e], t));
-                                    }
-#else
                                 const int jp = rows::load_code(codes_l, p.code_dtype, code_base - back * sk.codes_ld + row);
                                 replay_update8<NH>(cur, cb_l + (static_cast<long long>(jp) - static_cast<long long>(back) * p.K) * p.dp, lane);
-#endif
                             }
 #pragma unroll
                             for (int g = 0; g < NH; ++g)
