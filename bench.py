@@ -551,6 +551,7 @@ def main():
                                  "by install()), this rank's frames"},
         "decision_stats_semantic_stack": {"certified": [r[0] for r in st], "reranked": [r[1] for r in st],
                                           "full_scan": [r[2] for r in st],
+                                          "reranked_in_fp64": [r[3] for r in st],
                                           "single_stack_call_matches_two_stack_launch": single_matches},
     }
     if gather_ok is not None:

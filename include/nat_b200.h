@@ -84,9 +84,10 @@ size_t nat_rvq_workspace_bytes(const nat_rvq_codebooks* cb, int64_t n_frames);
 /* Per-layer counters written by nat_rvq_encode_f32 when stats_dev != NULL: uint64 [L][NAT_RVQ_STAT_FIELDS]. */
 #define NAT_RVQ_STAT_FIELDS 4
 enum nat_rvq_stat { NAT_STAT_CERTIFIED = 0,   /* frames decided by the tensor-core pass alone                  */
-                    NAT_STAT_RERANKED = 1,    /* frames whose top candidates were re-ranked exactly in fp64    */
+                    NAT_STAT_RERANKED = 1,    /* frames whose top candidates were re-ranked exactly            */
                     NAT_STAT_FULL_SCAN = 2,   /* frames that needed the exact full scan                        */
-                    NAT_STAT_RESERVED = 3 };
+                    NAT_STAT_RERANK_FP64 = 3  /* re-ranked frames (counted in RERANKED too) whose fp32 score
+                                                 intervals overlapped: settled in fp64 (fused stack kernel)   */ };
 
 /* Encode B*T frames through all L layers.
  *   x_dev            fp32 features in `layout`

@@ -1285,16 +1285,32 @@ int nat_rvq_encode_host_f32(const nat_rvq_codebooks* cb_const, const float* x_ho
 // ------------------------------------------------------------------------------------------------- front-end
 namespace {
 
+// A filterbank in the form the mel kernel reads, one device allocation of nat_mel_filterbank_bytes(n_mels):
+// band-major weights [n_mels, NBINS] and {first, one past last} non-zero bin per band (fb_to_banded_kernel), then the
+// projection layout and its tap-major weights (fb_layout_kernel).
+struct FbBlob {
+    size_t off_band, off_layout, off_wpack, bytes;
+    explicit FbBlob(int n_mels) {
+        off_band = static_cast<size_t>(round_up(static_cast<long long>(n_mels) * nat::fe::NBINS * 4, 256));
+        off_layout = off_band + static_cast<size_t>(round_up(static_cast<long long>(sizeof(int2)) * n_mels, 256));
+        off_wpack = off_layout + static_cast<size_t>(round_up(nat::fe::LAYOUT_INTS * 4LL, 256));
+        bytes = off_wpack + static_cast<size_t>(round_up(nat::fe::fb_wpack_capacity(n_mels) * 4, 256));
+    }
+    float* fbT(void* base) const { return reinterpret_cast<float*>(base); }
+    int2* band(void* base) const { return reinterpret_cast<int2*>(static_cast<char*>(base) + off_band); }
+    int* layout(void* base) const { return reinterpret_cast<int*>(static_cast<char*>(base) + off_layout); }
+    float* wpack(void* base) const { return reinterpret_cast<float*>(static_cast<char*>(base) + off_wpack); }
+};
+
 struct FePlan {
     float2* tw = nullptr;        // [NFFT/2]
-    float* fbT = nullptr;        // [n_mels, NBINS] built-in HTK filterbank, band-major
-    int2* band = nullptr;
+    char* fb = nullptr;          // built-in HTK filterbank in the prepared form (see FbBlob)
     int sm_count = 148;
     // cudaFuncAttributeMaxDynamicSharedMemorySize is per device: remembered per plan (plans are keyed by device)
     std::atomic<size_t> mel_smem_set{0};
     std::atomic<bool> spectral_smem_set{false};
     FePlan() = default;
-    FePlan(const FePlan& o) : tw(o.tw), fbT(o.fbT), band(o.band), sm_count(o.sm_count),
+    FePlan(const FePlan& o) : tw(o.tw), fb(o.fb), sm_count(o.sm_count),
                               mel_smem_set(o.mel_smem_set.load()), spectral_smem_set(o.spectral_smem_set.load()) {}
 };
 
@@ -1345,10 +1361,14 @@ int get_plan(int sample_rate, int n_mels, FePlan** out) {
             }
             band[m] = make_int2(std::min(lo, hi), hi);
         }
-        NAT_CUDA(cudaMalloc(&plan.fbT, fbT.size() * 4));
-        NAT_CUDA(cudaMalloc(&plan.band, sizeof(int2) * n_mels));
-        NAT_CUDA(cudaMemcpy(plan.fbT, fbT.data(), fbT.size() * 4, cudaMemcpyHostToDevice));
-        NAT_CUDA(cudaMemcpy(plan.band, band.data(), sizeof(int2) * n_mels, cudaMemcpyHostToDevice));
+        const FbBlob blob(n_mels);
+        NAT_CUDA(cudaMalloc(&plan.fb, blob.bytes));
+        NAT_CUDA(cudaMemcpy(blob.fbT(plan.fb), fbT.data(), fbT.size() * 4, cudaMemcpyHostToDevice));
+        NAT_CUDA(cudaMemcpy(blob.band(plan.fb), band.data(), sizeof(int2) * n_mels, cudaMemcpyHostToDevice));
+        nat::fe::fb_layout_kernel<<<1, nat::fe::MAX_MELS>>>(blob.fbT(plan.fb), blob.band(plan.fb), n_mels,
+                                                           blob.layout(plan.fb), blob.wpack(plan.fb));
+        NAT_CUDA(cudaGetLastError());
+        NAT_CUDA(cudaDeviceSynchronize());
     }
     auto ins = g_plans.emplace(key, plan);
     *out = &ins.first->second;
@@ -1363,24 +1383,26 @@ int64_t nat_spectral_num_frames(int64_t S, int n_fft, int hop) {
     return S >= n_fft ? 1 + (S - n_fft) / hop : 1;
 }
 
-// Banded form of a dense [n_fft/2+1, n_mels] filterbank: [n_mels, NBINS] band-major weights, then {first, one past
-// last} non-zero bin per band. Prepared once per transform object and handed to nat_mel_power_banded_f32.
-static size_t banded_weights_bytes(int n_mels) { return static_cast<size_t>(round_up(static_cast<long long>(n_mels) * nat::fe::NBINS * 4, 256)); }
+// Prepared form of a dense [n_fft/2+1, n_mels] filterbank (FbBlob): derived once per transform object and handed to
+// nat_mel_power_banded_f32.
+size_t nat_mel_filterbank_bytes(int n_mels) { return n_mels > 0 ? FbBlob(n_mels).bytes : 0; }
 
-size_t nat_mel_filterbank_bytes(int n_mels) {
-    return n_mels > 0 ? banded_weights_bytes(n_mels) + sizeof(int2) * static_cast<size_t>(n_mels) : 0;
+static int prepare_filterbank(const float* fb_dev, int n_mels, void* out_dev, cudaStream_t st) {
+    using namespace nat;
+    const FbBlob blob(n_mels);
+    NAT_LAUNCH(7, st, fe::fb_to_banded_kernel<<<n_mels, 128, 0, st>>>(fb_dev, n_mels, blob.fbT(out_dev), blob.band(out_dev)));
+    NAT_CUDA(cudaGetLastError());
+    NAT_LAUNCH(7, st, fe::fb_layout_kernel<<<1, fe::MAX_MELS, 0, st>>>(blob.fbT(out_dev), blob.band(out_dev), n_mels,
+                                                                     blob.layout(out_dev), blob.wpack(out_dev)));
+    NAT_CUDA(cudaGetLastError());
+    return NAT_OK;
 }
 
 int nat_mel_filterbank_prepare(const float* fb_dev, int n_mels, void* banded_out_dev, void* stream) {
     using namespace nat;
     if (fb_dev == nullptr || banded_out_dev == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null device pointer");
     if (n_mels < 1 || n_mels > fe::MAX_MELS) return fail(NAT_ERR_UNSUPPORTED, "unsupported n_mels %d", n_mels);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    char* base = static_cast<char*>(banded_out_dev);
-    NAT_LAUNCH(7, st, fe::fb_to_banded_kernel<<<n_mels, 128, 0, st>>>(fb_dev, n_mels, reinterpret_cast<float*>(base),
-                                                                   reinterpret_cast<int2*>(base + banded_weights_bytes(n_mels))));
-    NAT_CUDA(cudaGetLastError());
-    return NAT_OK;
+    return prepare_filterbank(fb_dev, n_mels, banded_out_dev, static_cast<cudaStream_t>(stream));
 }
 
 static int mel_power_impl(const float* wave_dev, int64_t B, int64_t S, int sample_rate, int n_fft, int hop, int n_mels,
@@ -1413,29 +1435,31 @@ static int mel_power_impl(const float* wave_dev, int64_t B, int64_t S, int sampl
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     fe::MelArgs p;
     p.wave = wave_dev; p.S = S; p.T = nat_mel_num_frames(S, hop); p.hop = hop; p.n_mels = n_mels; p.tw = plan->tw;
-    p.fbT = plan->fbT; p.band = plan->band; p.mel = mel_out_dev; p.logmel = logmel_out_dev;
+    p.mel = mel_out_dev; p.logmel = logmel_out_dev;
     p.inv_wsum = 1.0f / (3.0f * fe::NFFT / 8.0f);                 // sum of hann^2 over a period = 3N/8
-    // A caller-supplied filterbank is converted to the banded form into scratch that belongs to THIS call
-    // (stream-ordered allocation): concurrent calls on different streams never share it.
+    // A caller-supplied dense filterbank is prepared into scratch that belongs to THIS call (stream-ordered
+    // allocation): concurrent calls on different streams never share it.
+    const FbBlob blob(n_mels);
     char* fb_scratch = nullptr;
+    const void* fb_use = plan->fb;
     if (fb_banded_dev != nullptr) {
-        const char* base = static_cast<const char*>(fb_banded_dev);
-        p.fbT = reinterpret_cast<const float*>(base);
-        p.band = reinterpret_cast<const int2*>(base + banded_weights_bytes(n_mels));
+        fb_use = fb_banded_dev;
     } else if (fb_dev != nullptr) {
-        const size_t fbt_bytes = banded_weights_bytes(n_mels);
-        NAT_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&fb_scratch), fbt_bytes + sizeof(int2) * n_mels, st));
-        float* fbT_user = reinterpret_cast<float*>(fb_scratch);
-        int2* band_user = reinterpret_cast<int2*>(fb_scratch + fbt_bytes);
-        NAT_LAUNCH(7, st, fe::fb_to_banded_kernel<<<n_mels, 128, 0, st>>>(fb_dev, n_mels, fbT_user, band_user));
-        p.fbT = fbT_user; p.band = band_user;
+        NAT_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&fb_scratch), blob.bytes, st));
+        if (int rc = prepare_filterbank(fb_dev, n_mels, fb_scratch, st)) { cudaFreeAsync(fb_scratch, st); return rc; }
+        fb_use = fb_scratch;
     }
+    p.layout = blob.layout(const_cast<void*>(fb_use));
+    p.wpack = blob.wpack(const_cast<void*>(fb_use));
     const long long groups_per_clip = (p.T + fe::FRAMES_PER_CTA - 1) / fe::FRAMES_PER_CTA;
     const long long total = groups_per_clip * B;
     const size_t smem = fe::mel_smem_bytes(n_mels);
-    if (plan->mel_smem_set.load() < smem) {
-        NAT_CUDA(cudaFuncSetAttribute(fe::mel_power_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        plan->mel_smem_set.store(smem);
+    // The attribute belongs to the function (per device), not to a plan: every plan raises it to the same value, the
+    // largest any n_mels needs, so that no plan can lower it under another one's launch.
+    const size_t smem_cap = fe::mel_smem_bytes(fe::MAX_MELS);
+    if (plan->mel_smem_set.load() < smem_cap) {
+        NAT_CUDA(cudaFuncSetAttribute(fe::mel_power_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_cap)));
+        plan->mel_smem_set.store(smem_cap);
     }
     const int grid = static_cast<int>(std::min<long long>(total, plan->sm_count * 4LL * 4));
     NAT_LAUNCH(7, st, fe::mel_power_kernel<<<grid, fe::THREADS, smem, st>>>(p, groups_per_clip, total));

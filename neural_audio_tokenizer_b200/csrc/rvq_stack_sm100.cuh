@@ -214,6 +214,25 @@ __device__ __forceinline__ double score_regs(const float4 (&rv)[NV], const float
     return cn64 - 2.0 * acc;
 }
 
+// fp32 screening of one code: r.c and sum |r_i c_i| (what bounds its rounding error). Two FMA chains per lane and a
+// five-level tree: no partial sum is more than 2 NV + 6 <= 22 additions deep.
+template <int NV>
+__device__ __forceinline__ void score32_regs(const float4 (&rv)[NV], const float4 (&cv)[NV], float& dot, float& adot) {
+    float d0 = 0.f, d1 = 0.f, a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        {
+            const float4 b = cv[i];                    // zero beyond the row: adds nothing
+            d0 = fmaf(rv[i].x, b.x, d0); a0 = fmaf(fabsf(rv[i].x), fabsf(b.x), a0);
+            d1 = fmaf(rv[i].y, b.y, d1); a1 = fmaf(fabsf(rv[i].y), fabsf(b.y), a1);
+            d0 = fmaf(rv[i].z, b.z, d0); a0 = fmaf(fabsf(rv[i].z), fabsf(b.z), a0);
+            d1 = fmaf(rv[i].w, b.w, d1); a1 = fmaf(fabsf(rv[i].w), fabsf(b.w), a1);
+        }
+    }
+    dot = warp_sum(d0 + d1);
+    adot = warp_sum(a0 + a1);
+}
+
 template <int NV>
 __device__ __forceinline__ void load_row(float4 (&rv)[NV], const float4* __restrict__ r4, int dp4, int lane) {
 #pragma unroll
@@ -716,6 +735,7 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a0,  // fp16 [rows, dp]
             for (int l = 0; l < sk.L; ++l) {
                 const float* cb_l = sk.cbf + static_cast<long long>(l) * p.K * p.dp;
                 const double* cn64_l = sk.cn64 + static_cast<long long>(l) * p.K;
+                const float* cn32_l = sk.cn32 + static_cast<long long>(l) * p.kp;   // == fl32(cn64) for every code that can be a candidate
                 const bool last = l + 1 == sk.L;
                 const rows::LayerConst* lc_next = last ? nullptr : sk.lc + l + 1;
                 const float cabs = __ldg(&sk.lc[l].cabs);
@@ -760,7 +780,7 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a0,  // fp16 [rows, dp]
                     const unsigned n_mine = first_word & 0xFFFFu;
                     int jsel = static_cast<int>(first_word >> 16);
                     unsigned todo = __ballot_sync(0xffffffffu, lane < nrows && n_mine != 1u);
-                    unsigned n_rerank = 0, n_scan = 0;
+                    unsigned n_rerank = 0, n_scan = 0, n_fp64 = 0;
                     const unsigned n_cert = static_cast<unsigned>(nrows) - __popc(todo);
                     while (todo != 0) {
                         const int rr = __ffs(todo) - 1;
@@ -800,12 +820,45 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a0,  // fp16 [rows, dp]
                             }
                             ++n_scan;
                         } else {
+                            // Screening in fp32 first: lane c keeps an interval that contains candidate c's exact score
+                            // ||c||^2 - 2 r.c (|fl(r.c) - r.c| <= gamma_22 sum |r_i c_i|, gamma_22 < 1.4e-6, doubled by
+                            // the factor 2 and widened to 4.9e-6 to cover the rounding of the bound itself; 1.3e-7 of
+                            // ||c||^2 and |s| covers the roundings of fl32(||c||^2), of s and of the interval ends).
+                            // If the interval with the lowest upper end lies strictly below all the others, its code is
+                            // the fp64 answer. Otherwise (about one re-rank in 200) the candidates go through fp64.
+                            float lo_c = 0.f, hi_c = 0.f;
+                            int k_c = 0;
 #pragma unroll 1
                             for (int c = 0; c < static_cast<int>(n); ++c) {        // warp-uniform trip count, <= HCAP
                                 const int k = min(candidate(c), p.K - 1);
-                                const double s = score_regs<NV>(rv, reinterpret_cast<const float4*>(cb_l + static_cast<long long>(k) * p.dp),
-                                                                dp4, cn64_l[k], lane);
-                                if (bestj < 0 || s < best || (s == best && k < bestj)) { best = s; bestj = k; }
+                                float dot, adot;
+                                // (loading the first candidate together with the frame spills: 328 B, not adopted)
+                                float4 cv0[NV];
+                                load_code<NV>(cv0, reinterpret_cast<const float4*>(cb_l + static_cast<long long>(k) * p.dp), dp4, lane);
+                                score32_regs<NV>(rv, cv0, dot, adot);
+                                const float cn = __ldg(cn32_l + k);
+                                const float sc = fmaf(-2.f, dot, cn);
+                                const float e = fmaf(4.9e-6f, adot, 1.3e-7f * (cn + fabsf(sc))) + 1e-30f;
+                                if (lane == c) { lo_c = sc - e; hi_c = sc + e; k_c = k; }
+                            }
+                            const bool mine = lane < static_cast<int>(n);
+                            float hmin = mine ? hi_c : __int_as_float(0x7F800000);
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) hmin = fminf(hmin, __shfl_xor_sync(0xffffffffu, hmin, o));
+                            const unsigned win = __ballot_sync(0xffffffffu, mine && hi_c == hmin);
+                            const int wl = __ffs(win) - 1;
+                            const bool apart = !mine || lane == wl || lo_c > hmin;      // false on NaN: falls through
+                            if (__popc(win) == 1 && __all_sync(0xffffffffu, apart)) {
+                                bestj = __shfl_sync(0xffffffffu, k_c, wl);
+                            } else {
+#pragma unroll 1
+                                for (int c = 0; c < static_cast<int>(n); ++c) {
+                                    const int k = min(candidate(c), p.K - 1);
+                                    const double s = score_regs<NV>(rv, reinterpret_cast<const float4*>(cb_l + static_cast<long long>(k) * p.dp),
+                                                                    dp4, cn64_l[k], lane);
+                                    if (bestj < 0 || s < best || (s == best && k < bestj)) { best = s; bestj = k; }
+                                }
+                                ++n_fp64;
                             }
                             ++n_rerank;
                         }
@@ -960,6 +1013,7 @@ rvq_stack_kernel(const __grid_constant__ CUtensorMap map_a0,  // fp16 [rows, dp]
                             if (n_cert) atomicAdd(st + 0, static_cast<unsigned long long>(n_cert));
                             if (n_rerank) atomicAdd(st + 1, static_cast<unsigned long long>(n_rerank));
                             if (n_scan) atomicAdd(st + 2, static_cast<unsigned long long>(n_scan));
+                            if (n_fp64) atomicAdd(st + 3, static_cast<unsigned long long>(n_fp64));
                         }
                     }
                 }

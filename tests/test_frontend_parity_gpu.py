@@ -39,6 +39,13 @@ def test_mel_matches_torchaudio_golden(name):
                                      None))
     torch.cuda.synchronize()
     assert np.abs(out.cpu().numpy() - ref).max() <= MEL_TOL_BUILTIN * ref.max() + 1e-6
+    # the same entry point with the caller's dense filterbank (prepared inside the call)
+    out2 = torch.empty_like(mel)
+    fbc = mt.fb.contiguous()
+    _lib.check(lib.nat_mel_power_f32(wave.data_ptr(), 1, wave.numel(), sr, 2048, hop, 128, fbc.data_ptr(), out2.data_ptr(),
+                                     None, None))
+    torch.cuda.synchronize()
+    assert torch.equal(out2, mel)                                     # same kernel, same layout as the module's call
 
 
 def test_mel_batch_and_long_clip_vs_oracle():
@@ -52,6 +59,46 @@ def test_mel_batch_and_long_clip_vs_oracle():
         ref = (mel_oracle.stft_power(wave[b], 2048, 320).T @ fb).T
         assert mel[b].shape == ref.shape == (128, 1 + wave.shape[1] // 320)
         assert np.abs(mel[b] - ref).max() <= MEL_TOL_FB * ref.max() + 1e-7
+
+
+def _caller_filterbank(kind, n_mels, rng):
+    """Filterbanks that exercise every projection layout of csrc/mel_fft.cuh (dual / single, staged / through L1)."""
+    nb = 1025
+    fb = np.zeros((nb, n_mels), dtype=np.float32)
+    if kind == "wide_triangles":            # three bands overlap everywhere: not a two-band bank -> single layout
+        centres = np.linspace(20, 1000, n_mels)
+        half = 2.2 * (centres[1] - centres[0])
+        k = np.arange(nb)[:, None]
+        fb = np.maximum(0.0, 1.0 - np.abs(k - centres[None, :]) / half).astype(np.float32)
+    elif kind == "dense":                   # every bin in every band: weights stay in global memory
+        fb = rng.random((nb, n_mels), dtype=np.float32)
+    elif kind == "empty_band":              # a band of zeros in the middle, and one single-bin band at Nyquist
+        edges = np.linspace(0, 1024, n_mels + 1).astype(int)
+        for m in range(n_mels):
+            fb[edges[m]:edges[m + 1] + 1, m] = rng.random(edges[m + 1] + 1 - edges[m], dtype=np.float32)
+        fb[:, n_mels // 2] = 0.0
+        fb[:, n_mels - 1] = 0.0
+        fb[1024, n_mels - 1] = 1.0
+    return fb
+
+
+@pytest.mark.parametrize("kind,n_mels", [("htk", 80), ("htk", 40), ("htk", 200), ("wide_triangles", 128),
+                                         ("wide_triangles", 33), ("dense", 128), ("empty_band", 64), ("htk", 2)])
+def test_mel_projection_layouts_vs_oracle(kind, n_mels):
+    """The filterbank is a parameter of the transform (--n_mels, nat.py:5400; `fb` is a writable buffer): whatever its
+    shape, the projection must equal power @ fb."""
+    from neural_audio_tokenizer_b200 import MelSpectrogram
+    rng = np.random.default_rng(n_mels)
+    wave = (rng.standard_normal((2, 24000 + 77)) * 0.1).astype(np.float32)
+    mt = MelSpectrogram(sample_rate=24000, n_fft=2048, hop_length=320, n_mels=n_mels).cuda()
+    if kind != "htk":
+        mt.fb.copy_(torch.from_numpy(_caller_filterbank(kind, n_mels, rng)))
+    mel = mt(torch.from_numpy(wave).cuda()).cpu().numpy()
+    fb = mt.fb.cpu().numpy().astype(np.float64)
+    for b in range(2):
+        ref = (mel_oracle.stft_power(wave[b], 2048, 320).T @ fb).T
+        assert mel[b].shape == ref.shape
+        assert np.abs(mel[b] - ref).max() <= MEL_TOL_FB * ref.max() + 1e-7, (kind, n_mels)
 
 
 @pytest.mark.parametrize("name", ["spectral_tone_22050", "spectral_noise_24000", "spectral_short"])
