@@ -369,6 +369,10 @@ int nat_rvq_codebooks_create(const float* const* codebooks_dev, int L, int K, in
         }
         guard(cudaFuncSetAttribute(nat::rows::prep_bct_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    200 * 1024), "cudaFuncSetAttribute");
+        guard(cudaFuncSetAttribute(nat::rows::reconstruct_bct_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   200 * 1024), "cudaFuncSetAttribute");
+        guard(cudaFuncSetAttribute(nat::rows::reconstruct_bct_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   200 * 1024), "cudaFuncSetAttribute");
     }
     if (rc != NAT_OK) {
         nat_rvq_codebooks_destroy(cb);
@@ -581,23 +585,35 @@ static int encode_chunk(const EncodeCall& c, const Workspace& ws, const CUtensor
         sl.n_rows = n; sl.code_dtype = c.code_dtype;
         if (int rc = launch_fused_stack(sl, st)) return rc;
         if (extras) {
-            const int warps_grid = std::min((n + 7) / 8, cb->sm_count * 16);
-            NAT_LAUNCH(5, st, rows::reconstruct_rows_kernel<<<warps_grid, 256, 0, st>>>(
-                ws.r, c.quantized != nullptr ? ws.r_work : nullptr, n, cb->dp, cb->cbf, cb_layer_ld, cb->L, c.codes,
-                c.code_dtype, c.N, n0, c.want_loss ? ws.row_loss : nullptr, ws.rows));
-            if (c.want_loss)
-                for (int l = 0; l < cb->L; ++l)
-                    NAT_LAUNCH(4, st, rows::reduce_loss_kernel<<<1, 1024, 0, st>>>(ws.row_loss + static_cast<long long>(l) * ws.rows,
-                                                                                  n, ws.loss_acc + l));
-            if (c.quantized != nullptr) {
-                if (c.layout == NAT_LAYOUT_ROWS) {
-                    NAT_LAUNCH(5, st, rows::copy_rows_out_kernel<<<cb->sm_count * 8, 256, 0, st>>>(ws.r_work, n, cb->dp, cb->D,
-                                                                                                c.quantized + n0 * cb->D));
-                } else {
-                    dim3 grid((n + 31) / 32, (cb->D + 31) / 32);
-                    NAT_LAUNCH(5, st, rows::rows_to_bct_kernel<<<grid, 256, 0, st>>>(ws.r_work, cb->dp, c.T, cb->D, n0, n, c.quantized));
+            double* row_loss = c.want_loss ? ws.row_loss : nullptr;
+            const size_t tile_smem = static_cast<size_t>(rows::kReplayFrames) * cb->dp * sizeof(float);
+            if (c.quantized != nullptr && c.layout == NAT_LAYOUT_BCT && tile_smem <= 200 * 1024) {
+                // replay + transposed write in one pass: the [frames, Dp] intermediate is never written
+                const int n_tiles = (n + rows::kReplayFrames - 1) / rows::kReplayFrames;
+                const int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(2048 / rows::kReplayThreads, (220 * 1024) / (tile_smem + 1024))));
+                auto kern = cb->L == 4 ? rows::reconstruct_bct_kernel<4> : rows::reconstruct_bct_kernel<0>;
+                NAT_LAUNCH(5, st, kern<<<std::min(n_tiles, cb->sm_count * per_sm), rows::kReplayThreads, tile_smem, st>>>(
+                    ws.r, n, cb->dp, cb->D, cb->cbf, cb_layer_ld, cb->L, c.codes, c.code_dtype, c.N, n0, row_loss, ws.rows,
+                    c.T, n0, c.quantized));
+            } else {
+                const int warps_grid = std::min((n + 7) / 8, cb->sm_count * 16);
+                // [frames, D] output without padding: the replay writes the caller's rows directly
+                const bool direct = c.quantized != nullptr && c.layout == NAT_LAYOUT_ROWS && cb->dp == cb->D;
+                float* dst = c.quantized == nullptr ? nullptr : direct ? c.quantized + n0 * cb->D : ws.r_work;
+                NAT_LAUNCH(5, st, rows::reconstruct_rows_kernel<<<warps_grid, 256, 0, st>>>(
+                    ws.r, dst, n, cb->dp, cb->cbf, cb_layer_ld, cb->L, c.codes, c.code_dtype, c.N, n0, row_loss, ws.rows));
+                if (c.quantized != nullptr && !direct) {
+                    if (c.layout == NAT_LAYOUT_ROWS) {
+                        NAT_LAUNCH(5, st, rows::copy_rows_out_kernel<<<cb->sm_count * 8, 256, 0, st>>>(ws.r_work, n, cb->dp, cb->D,
+                                                                                                    c.quantized + n0 * cb->D));
+                    } else {
+                        dim3 grid((n + 31) / 32, (cb->D + 31) / 32);
+                        NAT_LAUNCH(5, st, rows::rows_to_bct_kernel<<<grid, 256, 0, st>>>(ws.r_work, cb->dp, c.T, cb->D, n0, n, c.quantized));
+                    }
                 }
             }
+            if (c.want_loss)
+                NAT_LAUNCH(4, st, rows::reduce_loss_kernel<<<cb->L, 1024, 0, st>>>(ws.row_loss, n, ws.loss_acc, ws.rows));
         }
         NAT_CUDA(cudaGetLastError());
         return NAT_OK;

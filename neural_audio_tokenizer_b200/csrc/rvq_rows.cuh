@@ -769,9 +769,12 @@ argmin_from_acc_kernel(UpdateArgs p, const float* __restrict__ acc, int acc_ld, 
 
 // ---------------------------------------------------------------------------------------------------- loss
 // Deterministic fixed-order sum of row_loss[0..n) added to *acc (one block).
+// Block b sums row_loss[b * ld ..] into acc[b]: all layers of a stack in one launch.
 __global__ void __launch_bounds__(1024)
-reduce_loss_kernel(const double* __restrict__ row_loss, int n, double* __restrict__ acc) {
+reduce_loss_kernel(const double* __restrict__ row_loss, int n, double* __restrict__ acc, long long ld = 0) {
     __shared__ double sh[1024];
+    row_loss += blockIdx.x * ld;
+    acc += blockIdx.x;
     double s = 0.0;
     for (int i = threadIdx.x; i < n; i += 1024) s += row_loss[i];
     sh[threadIdx.x] = s;
@@ -832,6 +835,94 @@ reconstruct_rows_kernel(const float* __restrict__ src, float* dst, int n, int dp
                 if (lane == 0) row_loss[l * loss_ld + row] = v;
             }
         }
+    }
+}
+// The same replay for the [B, D, T] form of the quantised sum (what ResidualVectorQuantizer.forward returns,
+// nat.py:1408-1415): a CTA replays 32 consecutive frames into a shared-memory tile and writes the tile transposed, so
+// the [frames, Dp] intermediate of reconstruct_rows_kernel + rows_to_bct_kernel (one write and one read of every
+// element) never exists. Tile: [32][dp] floats in 16-byte chunks, chunk c of frame f stored at chunk c ^ (f & 7):
+// the row-wise float4 stores (lane = chunk) and the column-wise float4 loads (lane = frame) are both conflict free.
+// Same arithmetic, in the same order, as reconstruct_rows_kernel. Dynamic smem: kReplayFrames * dp floats.
+constexpr int kReplayFrames = 32;
+constexpr int kReplayThreads = 512;         // two CTAs of 16 warps per SM next to a 96 KB tile each
+// LT > 0: the layer count as a compile-time constant (all code vectors of a chunk in flight together); 0: run-time L.
+template <int LT>
+__global__ void __launch_bounds__(kReplayThreads)
+reconstruct_bct_kernel(const float* __restrict__ src, int n, int dp, int D, const float* __restrict__ cb_all,
+                       long long cb_layer_ld, int L_rt, const void* __restrict__ codes, int code_dtype, long long codes_ld,
+                       long long code_off, double* __restrict__ row_loss, long long loss_ld, long long T, long long n0,
+                       float* __restrict__ out) {
+    extern __shared__ __align__(16) float replay_tile[];
+    float4* tile4 = reinterpret_cast<float4*>(replay_tile);
+    constexpr int LMAX = LT > 0 ? LT : 16;
+    const int L = LT > 0 ? LT : L_rt;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int dp4 = dp >> 2;
+    const int n_tiles = (n + kReplayFrames - 1) / kReplayFrames;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int f0 = tile * kReplayFrames;
+        for (int fr = warp; fr < kReplayFrames; fr += kReplayThreads / 32) {
+            const int row = f0 + fr;
+            if (row >= n) break;
+            const float4* s4 = reinterpret_cast<const float4*>(src + static_cast<long long>(row) * dp);
+            const float4* c4[LMAX];
+            double loss[LMAX];
+#pragma unroll
+            for (int l = 0; l < LMAX; ++l) {
+                if (l < L) {
+                    const int j = load_code(codes, code_dtype, l * codes_ld + code_off + row);
+                    c4[l] = reinterpret_cast<const float4*>(cb_all + l * cb_layer_ld + static_cast<long long>(j) * dp);
+                    loss[l] = 0.0;
+                }
+            }
+            for (int i = lane; i < dp4; i += 32) {
+                float4 rv = s4[i];
+                float4 cvs[LMAX];
+#pragma unroll
+                for (int l = 0; l < LMAX; ++l)
+                    if (LT > 0) cvs[l] = __ldg(c4[l] + i);
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int l = 0; l < LMAX; ++l) {
+                    if (l < L) {
+                        const float4 cv = LT > 0 ? cvs[l] : __ldg(c4[l] + i);
+                        float t, q;
+                        double ls = 0.0;
+                        t = __fsub_rn(cv.x, rv.x); q = __fadd_rn(rv.x, t); rv.x = __fsub_rn(rv.x, q); acc.x = l ? __fadd_rn(acc.x, q) : q; ls += static_cast<double>(__fmul_rn(t, t));
+                        t = __fsub_rn(cv.y, rv.y); q = __fadd_rn(rv.y, t); rv.y = __fsub_rn(rv.y, q); acc.y = l ? __fadd_rn(acc.y, q) : q; ls += static_cast<double>(__fmul_rn(t, t));
+                        t = __fsub_rn(cv.z, rv.z); q = __fadd_rn(rv.z, t); rv.z = __fsub_rn(rv.z, q); acc.z = l ? __fadd_rn(acc.z, q) : q; ls += static_cast<double>(__fmul_rn(t, t));
+                        t = __fsub_rn(cv.w, rv.w); q = __fadd_rn(rv.w, t); rv.w = __fsub_rn(rv.w, q); acc.w = l ? __fadd_rn(acc.w, q) : q; ls += static_cast<double>(__fmul_rn(t, t));
+                        if (row_loss != nullptr) loss[l] += ls;
+                    }
+                }
+                tile4[fr * dp4 + (i ^ (fr & 7))] = acc;
+            }
+            if (row_loss != nullptr) {
+#pragma unroll
+                for (int l = 0; l < LMAX; ++l) {
+                    if (l < L) {
+                        const double v = warp_sum(loss[l]);
+                        if (lane == 0) row_loss[l * loss_ld + row] = v;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // lane = frame: 32 consecutive t of one feature are one 128-byte run of the output
+        const int row = f0 + lane;
+        const long long g = n0 + row, b = g / T, t = g - b * T;
+        float* o = out + (b * D) * T + t;
+        for (int c = warp; c < dp4; c += kReplayThreads / 32) {
+            if (row < n) {
+                const float4 v = tile4[lane * dp4 + (c ^ (lane & 7))];
+                const int d = c * 4;
+                if (d + 0 < D) o[static_cast<long long>(d + 0) * T] = v.x;
+                if (d + 1 < D) o[static_cast<long long>(d + 1) * T] = v.y;
+                if (d + 2 < D) o[static_cast<long long>(d + 2) * T] = v.z;
+                if (d + 3 < D) o[static_cast<long long>(d + 3) * T] = v.w;
+            }
+        }
+        __syncthreads();
     }
 }
 __global__ void __launch_bounds__(256)
