@@ -373,6 +373,10 @@ int nat_rvq_codebooks_create(const float* const* codebooks_dev, int L, int K, in
                                    200 * 1024), "cudaFuncSetAttribute");
         guard(cudaFuncSetAttribute(nat::rows::reconstruct_bct_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    200 * 1024), "cudaFuncSetAttribute");
+        guard(cudaFuncSetAttribute(nat::rows::decode_bct_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   200 * 1024), "cudaFuncSetAttribute");
+        guard(cudaFuncSetAttribute(nat::rows::decode_bct_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   200 * 1024), "cudaFuncSetAttribute");
     }
     if (rc != NAT_OK) {
         nat_rvq_codebooks_destroy(cb);
@@ -869,6 +873,18 @@ int nat_rvq_decode_f32(const nat_rvq_codebooks* cb, const void* codes_dev, int c
     if (N <= 0) return NAT_OK;
     const int used = std::max(0, std::min(n_code_layers, cb->L));
     if (used > 0 && codes_dev == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null codes");
+    const size_t tile_smem = static_cast<size_t>(rows::kReplayFrames) * cb->dp * sizeof(float);
+    if (layout == NAT_LAYOUT_BCT && used > 0 && tile_smem <= 200 * 1024) {
+        const long long n_tiles = (N + rows::kReplayFrames - 1) / rows::kReplayFrames;
+        const int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(2048 / rows::kReplayThreads, (220 * 1024) / (tile_smem + 1024))));
+        auto kern = used == 4 ? rows::decode_bct_kernel<4> : rows::decode_bct_kernel<0>;
+        NAT_LAUNCH(5, static_cast<cudaStream_t>(stream),
+                   kern<<<static_cast<int>(std::min<long long>(n_tiles, cb->sm_count * per_sm)), rows::kReplayThreads, tile_smem,
+                          static_cast<cudaStream_t>(stream)>>>(cb->cbf, static_cast<long long>(cb->K) * cb->dp, cb->dp, cb->D, used,
+                                                               codes_dev, code_dtype, N, T, out_dev));
+        NAT_CUDA(cudaGetLastError());
+        return NAT_OK;
+    }
     const long long total = N * cb->D;
     const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, cb->sm_count * 16));
     NAT_LAUNCH(5, static_cast<cudaStream_t>(stream), rows::decode_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(

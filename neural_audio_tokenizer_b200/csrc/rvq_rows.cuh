@@ -935,6 +935,65 @@ copy_rows_out_kernel(const float* __restrict__ r, int n, int dp, int D, float* _
     }
 }
 
+// decode into [B, D, T]: a CTA sums the code vectors of 32 consecutive frames row-wise (coalesced 16-byte gathers) into
+// the swizzled tile of reconstruct_bct_kernel and writes it transposed in 128-byte runs. The element-per-thread kernel
+// below reads a 32-byte sector per 4-byte element in this layout (3.1 ms for 270 000 x 768 x 4 layers; this: see
+// profiles/). Same sum order: ((0 + c_0) + c_1) + ...
+template <int LT>
+__global__ void __launch_bounds__(kReplayThreads)
+decode_bct_kernel(const float* __restrict__ cb_all, long long cb_layer_ld, int dp, int D, int L_rt,
+                  const void* __restrict__ codes, int code_dtype, long long N, long long T, float* __restrict__ out) {
+    extern __shared__ __align__(16) float replay_tile[];
+    float4* tile4 = reinterpret_cast<float4*>(replay_tile);
+    constexpr int LMAX = LT > 0 ? LT : 16;
+    const int L = LT > 0 ? LT : L_rt;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int dp4 = dp >> 2;
+    const long long n_tiles = (N + kReplayFrames - 1) / kReplayFrames;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long f0 = tile * kReplayFrames;
+        for (int fr = warp; fr < kReplayFrames; fr += kReplayThreads / 32) {
+            const long long row = f0 + fr;
+            if (row >= N) break;
+            const float4* c4[LMAX];
+#pragma unroll
+            for (int l = 0; l < LMAX; ++l)
+                if (l < L) c4[l] = reinterpret_cast<const float4*>(cb_all + l * cb_layer_ld +
+                                                                    static_cast<long long>(load_code(codes, code_dtype, l * N + row)) * dp);
+            for (int i = lane; i < dp4; i += 32) {
+                float4 cvs[LMAX];
+#pragma unroll
+                for (int l = 0; l < LMAX; ++l)
+                    if (LT > 0) cvs[l] = __ldg(c4[l] + i);
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int l = 0; l < LMAX; ++l) {
+                    if (l < L) {
+                        const float4 cv = LT > 0 ? cvs[l] : __ldg(c4[l] + i);
+                        acc.x = __fadd_rn(acc.x, cv.x); acc.y = __fadd_rn(acc.y, cv.y);
+                        acc.z = __fadd_rn(acc.z, cv.z); acc.w = __fadd_rn(acc.w, cv.w);
+                    }
+                }
+                tile4[fr * dp4 + (i ^ (fr & 7))] = acc;
+            }
+        }
+        __syncthreads();
+        const long long row = f0 + lane, b = row / T, t = row - b * T;
+        float* o = out + (b * D) * T + t;
+        for (int c = warp; c < dp4; c += kReplayThreads / 32) {
+            if (row < N) {
+                const float4 v = tile4[lane * dp4 + (c ^ (lane & 7))];
+                const int d = c * 4;
+                if (d + 0 < D) o[static_cast<long long>(d + 0) * T] = v.x;
+                if (d + 1 < D) o[static_cast<long long>(d + 1) * T] = v.y;
+                if (d + 2 < D) o[static_cast<long long>(d + 2) * T] = v.z;
+                if (d + 3 < D) o[static_cast<long long>(d + 3) * T] = v.w;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // decode: out = ((0 + cb_0[code_0]) + cb_1[code_1]) + ...   (nat.py:1438-1444). One thread per output element.
 __global__ void __launch_bounds__(256)
 decode_kernel(const float* __restrict__ cb_all, long long cb_layer_ld, int dp, int D, int L_used,

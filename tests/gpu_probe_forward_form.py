@@ -18,3 +18,12 @@ for _ in range(5):
     out = rvq(x)
 e1.record(); torch.cuda.synchronize()
 print(f"forward form, one stack: {e0.elapsed_time(e1) / 5:.3f} ms", flush=True)
+codes = out[1]
+for _ in range(2):
+    dec = rvq.decode(codes)
+torch.cuda.synchronize()
+e0.record()
+for _ in range(5):
+    dec = rvq.decode(codes)
+e1.record(); torch.cuda.synchronize()
+print(f"decode, one stack ([1, {D}, {N}] out): {e0.elapsed_time(e1) / 5:.3f} ms  ({N * D * 4 / (e0.elapsed_time(e1) / 5) / 1e6:.0f} GB/s of output)", flush=True)

@@ -212,6 +212,32 @@ def test_decode_matches_oracle_and_roundtrip():
     assert torch.equal(again[0], codes[0])
 
 
+@pytest.mark.parametrize("B,T,D,K,L,used", [(3, 45, 64, 128, 4, 4), (2, 33, 50, 96, 3, 3), (1, 1000, 768, 1024, 4, 4),
+                                             (2, 70, 1024, 64, 6, 5), (1, 31, 36, 16, 2, 1)])
+def test_decode_shapes_vs_oracle(B, T, D, K, L, used):
+    """decode into [B, D, T] goes through a 32-frame tile: clips that end inside a tile, D that is no multiple of
+    4 or 32, fewer code lists than layers, every code dtype (nat.py:1438-1444)."""
+    from neural_audio_tokenizer_b200 import _lib
+    gen = torch.Generator().manual_seed(B * 1000 + T)
+    cbs = torch.randn(L, K, D, generator=gen)
+    codes = [torch.randint(0, K, (B, T), generator=gen) for _ in range(used)]
+    rvq = _dropin(cbs)
+    ref = rvq_oracle.rvq_decode(codes, list(cbs))
+    assert torch.equal(rvq.decode([c.cuda() for c in codes]).cpu(), ref)
+    # the C ABI with narrower index streams, both layouts
+    lib = _lib.load()
+    handle = rvq._pack.get(rvq._codebooks())
+    for dt, tdt in ((_lib.CODES_I32, torch.int32), (_lib.CODES_I16, torch.int16)):
+        cd = torch.stack(codes).reshape(used, B * T).to(tdt).cuda().contiguous()
+        out = torch.empty((B, D, T), device="cuda")
+        _lib.check(lib.nat_rvq_decode_f32(handle, cd.data_ptr(), dt, used, B, T, _lib.LAYOUT_BCT, out.data_ptr(), None))
+        rows = torch.empty((B * T, D), device="cuda")
+        _lib.check(lib.nat_rvq_decode_f32(handle, cd.data_ptr(), dt, used, B, T, _lib.LAYOUT_ROWS, rows.data_ptr(), None))
+        torch.cuda.synchronize()
+        assert torch.equal(out.cpu(), ref)
+        assert torch.equal(rows.reshape(B, T, D).transpose(1, 2).cpu(), ref)
+
+
 def test_vector_quantizer_single_layer_and_2d_input():
     from neural_audio_tokenizer_b200 import VectorQuantizer
     g = load_golden("rvq_small")
