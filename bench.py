@@ -503,6 +503,30 @@ def main():
         torch.cuda.synchronize()
     fwd_ms = e0.elapsed_time(e1) / 3
 
+    # ---- the reference's DEFAULT selection mode (sampling, nat.py:2150-2154) with device-side Philox noise -------
+    def sampling_step():
+        for s in stacks:
+            for q in s.quantizers:
+                q.use_stochastic = True
+            s.sampling_mode = "philox"
+            s.encode(x)
+    with torch.no_grad():
+        try:
+            for _ in range(2):
+                sampling_step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                sampling_step()
+            e1.record()
+            torch.cuda.synchronize()
+            smp_ms = e0.elapsed_time(e1) / 3
+        finally:
+            for s in stacks:
+                for q in s.quantizers:
+                    q.use_stochastic = False
+
     stats = torch.zeros((LAYERS_PER_STACK, _lib.STAT_FIELDS), dtype=torch.int64, device=device)
     ws1 = torch.empty(lib.nat_rvq_workspace_bytes(handles[0], n_local), dtype=torch.uint8, device=device)
     scratch = torch.empty((LAYERS_PER_STACK, n_local), dtype=torch.int16, device=device)
@@ -549,6 +573,10 @@ def main():
         "forward_form": {"value": n_local / (fwd_ms * 1e-3), "unit": "frames/s", "ms_per_step": fwd_ms,
                          "what": "rvq(x) for both stacks with the quantised sum and vq_loss (nat.py:3239-3240 as grafted "
                                  "by install()), this rank's frames"},
+        "sampling_form": {"value": n_local / (smp_ms * 1e-3), "unit": "frames/s", "ms_per_step": smp_ms,
+                          "what": "encode(x) of both stacks in the reference's default sampling mode (temperature 0.5), "
+                                  "sampling_mode 'philox': device noise, equal to the reference in distribution only "
+                                  "(tests/test_rvq_sampling_gpu.py); compare cpu_baseline_stochastic"},
         "decision_stats_semantic_stack": {"certified": [r[0] for r in st], "reranked": [r[1] for r in st],
                                           "full_scan": [r[2] for r in st],
                                           "reranked_in_fp64": [r[3] for r in st],

@@ -113,7 +113,8 @@ int nat_rvq_encode_f32(const nat_rvq_codebooks* cb, const float* x_dev, int layo
  *                      generator) -- codes then equal the reference's except at near-ties of probs / q; or NULL:
  *                      q comes from Philox4x32-10 keyed by philox_seed (counter: frame, code, philox_draw + layer),
  *                      equal to the reference in distribution only. In this mode the distances come from the
- *                      tensor-core pass (bulk throughput; a score matrix of B*T x K floats is allocated stream-ordered)
+ *                      tensor-core pass (bulk throughput; the score matrix, chunk frames x K floats, is carved off
+ *                      the tail of the workspace and the chunk shrinks until both fit: nothing is allocated)
  *                      unless flags has NAT_RVQ_EXACT_SCAN, which keeps the exact per-frame scan
  * Outputs as nat_rvq_encode_f32. */
 int nat_rvq_sample_f32(const nat_rvq_codebooks* cb, const float* x_dev, int layout, int64_t B, int64_t T,

@@ -373,6 +373,8 @@ int nat_rvq_codebooks_create(const float* const* codebooks_dev, int L, int K, in
                                    200 * 1024), "cudaFuncSetAttribute");
         guard(cudaFuncSetAttribute(nat::rows::reconstruct_bct_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    200 * 1024), "cudaFuncSetAttribute");
+        guard(cudaFuncSetAttribute(nat::rows::sample_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
+              "cudaFuncSetAttribute");
         guard(cudaFuncSetAttribute(nat::rows::decode_bct_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    200 * 1024), "cudaFuncSetAttribute");
         guard(cudaFuncSetAttribute(nat::rows::decode_bct_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -744,8 +746,24 @@ static int encode_impl(const nat_rvq_codebooks* cb_const, const float* x_dev, in
     const int n_lanes = two ? 2 : 1;
     Workspace ws[2];
     CUtensorMap map_a[2];
+    long long want = std::min<long long>((N + n_lanes - 1) / n_lanes, chunk_cap_rows());
+    // Philox sampling reads its distances from a score matrix [frames, Kp] (the tensor-core pass dumps its
+    // accumulators): it lives in the tail of the caller's workspace, and the chunk shrinks until both fit. (A
+    // stream-ordered allocation per call cost 5-260 ms of host time: the default pool hands the gigabyte back to the
+    // driver at every synchronisation.)
+    const bool philox_bulk = temperatures != nullptr && noise_dev == nullptr && !(flags & NAT_RVQ_EXACT_SCAN);
+    if (philox_bulk) {
+        const size_t per_row = ws_per_row(cb->dp, cb->L) + static_cast<size_t>(cb->kp) * sizeof(float);
+        const size_t fixed = kWsFixed + 256 * 10 + 512;
+        const long long fit = workspace_bytes > fixed ? static_cast<long long>((workspace_bytes - fixed) / per_row) / 128 * 128 : 0;
+        if (fit < 128)
+            return fail(NAT_ERR_WORKSPACE, "workspace of %zu bytes cannot hold one 128-frame tile and its score rows (need %zu)",
+                        workspace_bytes, fixed + 128 * per_row);
+        want = std::min(round_up(want, 128), fit);
+        scores_bytes = static_cast<size_t>(want) * cb->kp * sizeof(float);
+        workspace_bytes = (workspace_bytes - scores_bytes) & ~static_cast<size_t>(255);
+    }
     const size_t half_bytes = (workspace_bytes / n_lanes) & ~static_cast<size_t>(255);
-    const long long want = std::min<long long>((N + n_lanes - 1) / n_lanes, chunk_cap_rows());
     for (int i = 0; i < n_lanes; ++i) {
         if (!carve(static_cast<char*>(workspace_dev) + i * half_bytes, half_bytes, cb->dp, cb->L, want, &ws[i]))
             return fail(NAT_ERR_WORKSPACE, "workspace of %zu bytes cannot hold one 128-frame tile per lane (need %zu)",
@@ -770,14 +788,8 @@ static int encode_impl(const nat_rvq_codebooks* cb_const, const float* x_dev, in
     call.temperatures = temperatures; call.noise = noise_dev; call.seed = seed; call.draw_base = draw_base;
     // Score matrix (accumulator dump): the Philox sampling path, and the small-input argmin path -- inputs whose
     // tiles x codebook chunks fit one wave of SMs would otherwise run a whole stack on a few persistent CTAs.
-    bool scores_owned = false;
-    if (scores_bytes != 0) {
+    if (scores_bytes != 0)
         call.scores = reinterpret_cast<float*>(static_cast<char*>(workspace_dev) + workspace_bytes);   // the tail cut off above
-    } else if (temperatures != nullptr && noise_dev == nullptr && !call.exact) {
-        const size_t bytes = static_cast<size_t>(ws[0].rows) * cb->kp * sizeof(float);
-        NAT_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&call.scores), bytes, st));
-        scores_owned = true;
-    }
     for (int i = 0; i < n_lanes; ++i) {
         if (loss_out_dev != nullptr) NAT_CUDA(cudaMemsetAsync(ws[i].loss_acc, 0, sizeof(double) * cb->L, lane_st[i]));
         if (cb->dp != cb->D) NAT_CUDA(cudaMemsetAsync(ws[i].a, 0, static_cast<size_t>(ws[i].rows) * cb->dp * 2, lane_st[i]));
@@ -794,7 +806,6 @@ static int encode_impl(const nat_rvq_codebooks* cb_const, const float* x_dev, in
             NAT_CUDA(cudaStreamWaitEvent(st, cb->side_ev[1 + i], 0));
         }
     }
-    if (scores_owned) NAT_CUDA(cudaFreeAsync(call.scores, st));
     if (loss_out_dev != nullptr) {
         NAT_LAUNCH(4, st, rows::finish_loss_kernel<<<1, 32, 0, st>>>(ws[0].loss_acc, two ? ws[1].loss_acc : nullptr, cb->L,
                                                                    static_cast<double>(N) * cb->D, commitment_weight,
@@ -825,7 +836,8 @@ int nat_rvq_sample_f32(const nat_rvq_codebooks* cb, const float* x_dev, int layo
     const size_t smem = static_cast<size_t>(cb->dp) * 4 + static_cast<size_t>(cb->K) * 4;
     if (smem > 200 * 1024)
         return fail(NAT_ERR_UNSUPPORTED, "sampling mode keeps K scores in shared memory: codebook_size %d is too large", cb->K);
-    NAT_CUDA(cudaFuncSetAttribute(nat::rows::sample_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    // (sample_scan_kernel's shared-memory limit is raised once per device when a codebook handle is created: the
+    // attribute call costs milliseconds of host time, 5.5 of the 12.7 ms this call took on 270 000 frames)
     return encode_impl(cb, x_dev, layout, B, T, codes_out_dev, code_dtype, quantized_out_dev, loss_out_dev,
                        commitment_weight, nullptr, workspace_dev, workspace_bytes,
                        NAT_RVQ_SINGLE_STREAM | (flags & NAT_RVQ_EXACT_SCAN), stream,
