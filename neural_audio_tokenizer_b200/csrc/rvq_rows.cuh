@@ -518,7 +518,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t (&ctr)[4], uint32_t k0, u
 // the smallest positive value the formula can produce so that p / q stays finite.
 __device__ __forceinline__ float exp1_from_bits(uint32_t bits) {
     const float u = (static_cast<float>(bits >> 8) + 1.0f) * (1.0f / 16777216.0f);
-    const float q = -logf(u);
+    const float q = -__logf(u);           // MUFU.LG2 * ln 2: the draw is noise, two ulps of it do not matter
     return q > 0.f ? q : 5.9604645e-8f;
 }
 
@@ -675,8 +675,9 @@ sample_from_acc_kernel(UpdateArgs p, SampleArgs sa, const float* __restrict__ ac
             for (int e = 0; e < 4; ++e) {
                 const int k = k4 * 4 + e;
                 if (k < p.K) {
-                    const float d = sqrtf(fmaxf(fmaf(av[e], alpha, cv[e]) + xnf, 0.f));
-                    const float v = -d * inv_t - logf(exp1_from_bits(ctr[e]));
+                    float d;                                        // sqrt.approx: 1 ulp, one MUFU instead of a Newton step
+                    asm("sqrt.approx.f32 %0, %1;" : "=f"(d) : "f"(fmaxf(fmaf(av[e], alpha, cv[e]) + xnf, 0.f)));
+                    const float v = -d * inv_t - __logf(exp1_from_bits(ctr[e]));
                     if (v > bv) { bv = v; bi = k; }                 // k ascending per lane: first maximum kept
                 }
             }
