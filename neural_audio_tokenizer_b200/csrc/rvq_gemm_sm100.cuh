@@ -185,10 +185,14 @@ rvq_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_a,   // fp16 [rows,
                     tmem_wait_ld();
                     if (DUMP) {
                         if (row < n_rows) {
-                            // one full 128-byte line per thread, as eight 16-byte stores (dump_ld is a multiple of 256)
-                            uint4* out = reinterpret_cast<uint4*>(dump + static_cast<long long>(row) * dump_ld + chunk * BLOCK_N + g * 32);
+                            // one full 128-byte line per thread, as four 32-byte stores: whole sectors (dump_ld is a
+                            // multiple of 256; two 16-byte halves of a sector from two instructions cost L2 a merge)
+                            float* out = dump + static_cast<long long>(row) * dump_ld + chunk * BLOCK_N + g * 32;
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) out[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            for (int j = 0; j < 4; ++j)
+                                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                                             ::"l"(out + 8 * j), "r"(v[8 * j]), "r"(v[8 * j + 1]), "r"(v[8 * j + 2]), "r"(v[8 * j + 3]),
+                                               "r"(v[8 * j + 4]), "r"(v[8 * j + 5]), "r"(v[8 * j + 6]), "r"(v[8 * j + 7]) : "memory");
                         }
                     } else {
 #pragma unroll
