@@ -217,6 +217,34 @@ def cpu_arm(x, steps: int = 1, warmup: int = 0, keep_codes: bool = False):
     return x.shape[-1] * len(times) / total, total / len(times), kind, codes
 
 
+def reference_on_gpu_block(x_dev):
+    """The UNMODIFIED reference's own RVQ forward (torch ops: cdist, argmin, embedding) on the SAME GPU and inputs:
+    what moving the reference to cuda buys without this library. Reported beside the CPU arm, never as the baseline."""
+    ref = reference_stacks()
+    if ref is None:
+        return {"unavailable": "reference not carried (baseline/_ref)"}
+    ref = [s.to(x_dev.device) for s in ref]
+    def step():
+        with torch.no_grad():
+            for s in ref:
+                s(x_dev)
+    try:
+        step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+    except torch.cuda.OutOfMemoryError as e:
+        return {"unavailable": f"out of memory: {str(e)[:80]}"}
+    ms = e0.elapsed_time(e1) / 3
+    return {"value": x_dev.shape[-1] / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms,
+            "what": "the unmodified reference's ResidualVectorQuantizer.forward (argmin mode, both stacks, quantised sum "
+                    "and losses: compare forward_form) as torch eager ops on this GPU, same inputs"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -596,6 +624,7 @@ def main():
                                               f"pass, {sec:.1f} s, {cores} threads of {os.cpu_count()} logical CPUs; its "
                                               "codes are the parity block's reference"}
             line["cpu_baseline_stochastic"] = stochastic_cpu_block(x_host)
+            line["reference_on_this_gpu"] = reference_on_gpu_block(x)
             line["frontend"] = frontend_block(device, peaks)
         if par["real_mismatches"] > 0:
             emit(line)
