@@ -419,7 +419,14 @@ def main():
     ws_bytes = lib.nat_rvq_stacks_workspace_bytes(harr, 2, n_local)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
     stream = torch.cuda.current_stream(device)
-    gatherer = CodeGatherer(L_total, n_local, world, device) if world > 1 else None
+    # index all-gather: copy engines over NVLink peer memory (no kernel beside the persistent stack kernel);
+    # NAT_BENCH_GATHER=nccl keeps NCCL's all_gather_into_tensor on a side stream
+    gather_kind = os.environ.get("NAT_BENCH_GATHER", "peer") if world > 1 else None
+    if gather_kind == "peer":
+        from neural_audio_tokenizer_b200.sharding import PeerCodeGatherer
+        gatherer = PeerCodeGatherer(L_total, n_local, world, device)
+    else:
+        gatherer = CodeGatherer(L_total, n_local, world, device) if world > 1 else None
 
     def step():
         encode_stacks(stacks, x, torch.int16, out=codes, workspace=ws)
@@ -461,6 +468,8 @@ def main():
                   "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                   "gpu_launches": int(launches), "kernel_only": True, "build_id": build_id()})
         if world > 1:
+            if hasattr(gatherer, "close"):
+                gatherer.close()
             dist.destroy_process_group()
         return
 
@@ -580,7 +589,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": f"synthetic 1 h clip per GPU: {n_local} frames x {DIM}-d fp32 features (75 Hz), 4+4 RVQ "
                                f"layers, codebook {CODEBOOK}, argmin mode, int16 index streams"
-                               + (", NCCL all-gather of the index streams" if world > 1 else ""),
+                               + (", all-gather of the index streams" if world > 1 else ""),
                    "frames_per_gpu": n_local, "dim": DIM, "codebook_size": CODEBOOK, "layers": L_total,
                    "l2": "inputs larger than L2 (0.83 GB features per GPU, 126 MB L2)",
                    "parallelism": f"frame-sharded x{world}, replicated codebooks", "build_id": build_id()},
@@ -612,6 +621,9 @@ def main():
     }
     if gather_ok is not None:
         line["all_gather"] = {"ok": gather_ok, "bytes_per_rank": L_total * n_local * 2,
+                              "transport": ("copy engines over NVLink peer memory (nat_peer_all_gather: 2-D peer copies into "
+                                            "every rank's final layout, stream memory operations as the barrier; no kernel)"
+                                            if gather_kind == "peer" else "NCCL all_gather_into_tensor + one strided copy"),
                               "overlap": "issued on a side stream per step; the next step's kernels do not wait for it"}
     if not args.no_cpu_baseline:
         cores = host_threads()
@@ -632,6 +644,8 @@ def main():
     emit(line)
     if world > 1:
         dist.barrier()
+        if hasattr(gatherer, "close"):
+            gatherer.close()
         dist.destroy_process_group()
 
 

@@ -296,6 +296,25 @@ int nat_debug_rvq_scores(const nat_rvq_codebooks* cb, int layer, const float* ro
 int nat_debug_stack_counters(nat_rvq_codebooks* cb, int enable, unsigned long long* out_host, int max_ctas,
                              int* n_ctas, int* n_slots);
 
+/* ---- all-gather of the index streams over NVLink peer memory (one process per GPU; csrc/peer_exchange.inc) ----------
+ * Replaces the `dist.all_gather` a sharded run would issue on the [L, frames] index streams (the
+ * reference itself is single-device). Every rank's [rows, col_bytes] block is written by the copy engines straight
+ * into its column range of every rank's [rows, world * col_bytes] output; no kernel, no staging on the receiver.
+ *   nat_peer_create      allocates this rank's two output buffers and step counters on the current device
+ *   nat_peer_export      writes two CUDA IPC handles (128 bytes) to hand to the other ranks (any transport)
+ *   nat_peer_connect     handles_all = the world's 128-byte records in rank order
+ *   nat_peer_all_gather  stream-ordered: pushes `block_dev` (row pitch `block_pitch` bytes) to every rank, then makes
+ *                        `stream` wait until every rank's block of this step has landed here; *gathered_out = the
+ *                        output buffer of this step (valid, in stream order, until the call after next)
+ * Collective: every rank must make the same sequence of all_gather calls. */
+typedef struct nat_peer_ctx nat_peer_ctx;
+int nat_peer_create(int world, int rank, size_t rows, size_t col_bytes, nat_peer_ctx** out);
+int nat_peer_export(const nat_peer_ctx* ctx, void* handles_out_128_bytes);
+int nat_peer_connect(nat_peer_ctx* ctx, const void* handles_all);
+int nat_peer_all_gather(nat_peer_ctx* ctx, const void* block_dev, size_t block_pitch, void* stream, void** gathered_out);
+void* nat_peer_buffer(const nat_peer_ctx* ctx, int which);
+void nat_peer_destroy(nat_peer_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif

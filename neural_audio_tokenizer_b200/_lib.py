@@ -71,7 +71,14 @@ _SIGNATURES = [
                                        c_char_p, ctypes.c_double, POINTER(c_void_p), POINTER(c_size_t)]),
     ("nat_free_host", None, [c_void_p]),
     ("nat_debug_stack_counters", c_int, [c_void_p, c_int, c_void_p, c_int, POINTER(c_int), POINTER(c_int)]),
+    ("nat_peer_create", c_int, [c_int, c_int, c_size_t, c_size_t, POINTER(c_void_p)]),
+    ("nat_peer_export", c_int, [c_void_p, c_void_p]),
+    ("nat_peer_connect", c_int, [c_void_p, c_void_p]),
+    ("nat_peer_all_gather", c_int, [c_void_p, c_void_p, c_size_t, c_void_p, POINTER(c_void_p)]),
+    ("nat_peer_buffer", c_void_p, [c_void_p, c_int]),
+    ("nat_peer_destroy", None, [c_void_p]),
 ]
+PEER_HANDLE_BYTES = 128
 EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]
 
 _lib = None

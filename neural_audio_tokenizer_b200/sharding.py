@@ -105,3 +105,94 @@ class CodeGatherer:
         for k in range(2):
             if self.used[k]:
                 cur.wait_event(self.done[k])
+
+
+class _DeviceArray:
+    """A raw device allocation of the native library seen as a torch tensor (__cuda_array_interface__, no copy)."""
+
+    def __init__(self, ptr: int, shape, typestr: str, owner):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3}
+        self._owner = owner
+
+
+class PeerCodeGatherer:
+    """`CodeGatherer` without a collective kernel: every rank's [L, n_local] index streams are written by the copy
+    engines over NVLink straight into their column range of every rank's [L, world * per] output
+    (nat_peer_all_gather, csrc/peer_exchange.inc). No SM is involved, so the exchange does not compete with the
+    persistent stack kernel of the next step the way NCCL's all-gather kernel does. One process per GPU on one box
+    (CUDA IPC); torch.distributed is used once, to pass the IPC handles around.
+
+    Same interface as CodeGatherer: `all_gather(local)` stages the rank's streams on the caller's stream, runs the
+    exchange on a side stream and returns the output tensor of this step, valid after `wait()` (or in the side
+    stream's order); outputs are double buffered."""
+
+    def __init__(self, n_layers: int, n_local: int, world: int, device, n_total: int = None, group=None):
+        from . import _lib
+        self._lib_mod = _lib
+        lib = _lib.load()
+        self.L, self.world, self.group = n_layers, world, group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n_total = n_total if n_total is not None else n_local * world
+        self.per = -(-self.n_total // world)
+        self.n_local = n_local
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("PeerCodeGatherer moves device memory over NVLink: it needs CUDA devices (CodeGatherer "
+                               "runs on any torch.distributed backend)")
+        import ctypes
+        self._ctx = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.nat_peer_create(world, self.rank, n_layers, self.per * 2, ctypes.byref(self._ctx)))
+            mine = (ctypes.c_ubyte * _lib.PEER_HANDLE_BYTES)()
+            _lib.check(lib.nat_peer_export(self._ctx, mine))
+            if world > 1:
+                send = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(self.device)
+                recv = torch.empty(world * _lib.PEER_HANDLE_BYTES, dtype=torch.uint8, device=self.device)
+                dist.all_gather_into_tensor(recv, send, group=group)
+                blob = bytes(recv.cpu().numpy().tobytes())
+                _lib.check(lib.nat_peer_connect(self._ctx, ctypes.c_char_p(blob)))
+                dist.barrier(group=group)                       # every rank has opened every buffer before the first push
+        self.out = [torch.as_tensor(_DeviceArray(lib.nat_peer_buffer(self._ctx, k), (n_layers, world * self.per), "<i2", self),
+                                    device=self.device) for k in range(2)]
+        self.comm = torch.cuda.Stream(device=self.device)
+        self.send = [torch.zeros((n_layers, self.per), dtype=torch.int16, device=self.device) for _ in range(2)]
+        self.staged = [torch.cuda.Event() for _ in range(2)]
+        self.done = [torch.cuda.Event() for _ in range(2)]
+        self.used = [False, False]
+        self.i = 0
+
+    def all_gather(self, local_codes: torch.Tensor) -> torch.Tensor:
+        import ctypes
+        if tuple(local_codes.shape) != (self.L, self.n_local):
+            raise ValueError(f"expected [{self.L}, {self.n_local}] index streams, got {tuple(local_codes.shape)}")
+        lib = self._lib_mod.load()
+        self.i += 1
+        k = self.i & 1                                          # the library's buffer of step i is buffer i & 1
+        cur = torch.cuda.current_stream(self.device)
+        if self.used[k]:
+            cur.wait_event(self.done[k])                        # the staging buffer's previous exchange has been sent
+        self.send[k][:, :self.n_local].copy_(local_codes)
+        self.staged[k].record(cur)
+        self.comm.wait_event(self.staged[k])
+        got = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            self._lib_mod.check(lib.nat_peer_all_gather(self._ctx, self.send[k].data_ptr(), self.per * 2,
+                                                        self.comm.cuda_stream, ctypes.byref(got)))
+        assert got.value == self.out[k].data_ptr()
+        self.done[k].record(self.comm)
+        self.used[k] = True
+        return self.out[k][:, :self.n_total] if self.world * self.per != self.n_total else self.out[k]
+
+    def wait(self) -> None:
+        cur = torch.cuda.current_stream(self.device)
+        for k in range(2):
+            if self.used[k]:
+                cur.wait_event(self.done[k])
+
+    def close(self) -> None:
+        if self._ctx:
+            torch.cuda.synchronize(self.device)
+            if dist.is_initialized() and self.world > 1:
+                dist.barrier(group=self.group)                  # nobody unmaps a buffer a peer may still write
+            self._lib_mod.load().nat_peer_destroy(self._ctx)
+            self._ctx = None
