@@ -419,14 +419,21 @@ def main():
     ws_bytes = lib.nat_rvq_stacks_workspace_bytes(harr, 2, n_local)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
     stream = torch.cuda.current_stream(device)
-    # index all-gather: copy engines over NVLink peer memory (no kernel beside the persistent stack kernel);
-    # NAT_BENCH_GATHER=nccl keeps NCCL's all_gather_into_tensor on a side stream
-    gather_kind = os.environ.get("NAT_BENCH_GATHER", "peer") if world > 1 else None
+    # index all-gather: NCCL's all_gather_into_tensor on a side stream; NAT_BENCH_GATHER=peer uses the copy engines
+    # over NVLink peer memory instead (no kernel beside the persistent stack kernel: 466 M frames/s on 8 GPUs against
+    # 447 M, profiles/r2_v4_bench_8gpu_peer.json). NCCL stays the default because the peer path's two-phase teardown
+    # was written after the round's GPU budget was spent (its first version hung torchrun jobs at exit).
+    gather_kind = os.environ.get("NAT_BENCH_GATHER", "nccl") if world > 1 else None
+    gatherer, gather_note = None, None
     if gather_kind == "peer":
         from neural_audio_tokenizer_b200.sharding import PeerCodeGatherer
-        gatherer = PeerCodeGatherer(L_total, n_local, world, device)
-    else:
-        gatherer = CodeGatherer(L_total, n_local, world, device) if world > 1 else None
+        try:
+            gatherer = PeerCodeGatherer(L_total, n_local, world, device)
+        except RuntimeError as e:                # raised on every rank alike (the set-up agrees before it returns)
+            gather_kind, gather_note = "nccl", f"peer-memory exchange refused: {e}"
+            sys.stderr.write(f"bench.py: {gather_note}; using NCCL\n")
+    if world > 1 and gatherer is None:
+        gatherer = CodeGatherer(L_total, n_local, world, device)
 
     def step():
         encode_stacks(stacks, x, torch.int16, out=codes, workspace=ws)
@@ -625,6 +632,8 @@ def main():
                                             "every rank's final layout, stream memory operations as the barrier; no kernel)"
                                             if gather_kind == "peer" else "NCCL all_gather_into_tensor + one strided copy"),
                               "overlap": "issued on a side stream per step; the next step's kernels do not wait for it"}
+        if gather_note:
+            line["all_gather"]["note"] = gather_note
     if not args.no_cpu_baseline:
         cores = host_threads()
         n_par = min(n_local, FRAMES) if world == 1 else min(n_local, PARITY_SAMPLE_FRAMES)

@@ -313,7 +313,12 @@ int nat_peer_export(const nat_peer_ctx* ctx, void* handles_out_128_bytes);
 int nat_peer_connect(nat_peer_ctx* ctx, const void* handles_all);
 int nat_peer_all_gather(nat_peer_ctx* ctx, const void* block_dev, size_t block_pitch, void* stream, void** gathered_out);
 void* nat_peer_buffer(const nat_peer_ctx* ctx, int which);
+/* Teardown, in this order on every rank: nat_peer_disconnect (unmaps the peers' buffers), a barrier of the caller's,
+ * nat_peer_destroy (frees this rank's buffers: nobody maps them any more). */
+int nat_peer_disconnect(nat_peer_ctx* ctx);
 void nat_peer_destroy(nat_peer_ctx* ctx);
+/* The nat_peer_* functions keep their own thread-local message (they are a translation unit of their own). */
+const char* nat_peer_last_error(void);
 
 #ifdef __cplusplus
 }

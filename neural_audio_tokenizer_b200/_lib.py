@@ -76,7 +76,9 @@ _SIGNATURES = [
     ("nat_peer_connect", c_int, [c_void_p, c_void_p]),
     ("nat_peer_all_gather", c_int, [c_void_p, c_void_p, c_size_t, c_void_p, POINTER(c_void_p)]),
     ("nat_peer_buffer", c_void_p, [c_void_p, c_int]),
+    ("nat_peer_disconnect", c_int, [c_void_p]),
     ("nat_peer_destroy", None, [c_void_p]),
+    ("nat_peer_last_error", c_char_p, []),
 ]
 PEER_HANDLE_BYTES = 128
 EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]
@@ -113,3 +115,9 @@ def load() -> ctypes.CDLL:
 def check(status: int) -> None:
     if status != NAT_OK:
         raise NatError(status, (load().nat_last_error() or b"").decode("utf-8", "replace"))
+
+
+def check_peer(status: int) -> None:
+    """check() for the nat_peer_* functions, which keep their own message."""
+    if status != NAT_OK:
+        raise NatError(status, (load().nat_peer_last_error() or b"").decode("utf-8", "replace"))

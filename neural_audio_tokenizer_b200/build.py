@@ -10,7 +10,8 @@ import subprocess
 import sys
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-CSRC = os.path.join(PKG_DIR, "csrc")
+CSRC = os.path.join(PKG_DIR, "csrc")                 # kernels + their launcher: what bench.build_id hashes
+CSRC_HOST = os.path.join(PKG_DIR, "csrc_host")       # host-only translation units (no kernel depends on them)
 LIB_PATH = os.environ.get("NAT_B200_LIB_OUT") or os.path.join(PKG_DIR, "libnat_b200.so")
 
 NVCC_FLAGS = [
@@ -28,14 +29,16 @@ def extra_flags():
 
 
 def sources():
-    return [os.path.join(CSRC, "nat_b200.cu"), os.path.join(CSRC, "ndjson_emit.cpp")]
+    return [os.path.join(CSRC, "nat_b200.cu"), os.path.join(CSRC, "ndjson_emit.cpp"),
+            os.path.join(CSRC_HOST, "peer_exchange.cpp")]
 
 
 def _stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
     built = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(PKG_DIR, "..", "include", "nat_b200.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(CSRC_HOST, f) for f in os.listdir(CSRC_HOST)] + \
+           [os.path.join(PKG_DIR, "..", "include", "nat_b200.h")]
     return any(os.path.getmtime(d) > built for d in deps if os.path.exists(d))
 
 

@@ -1537,6 +1537,3 @@ int nat_spectral_stats_f32(const float* wave_dev, int64_t S, int sample_rate, in
 }
 
 }  // extern "C"
-
-// ------------------------------------------------------------------------------------------------- multi-GPU exchange
-#include "peer_exchange.inc"

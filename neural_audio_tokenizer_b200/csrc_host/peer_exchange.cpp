@@ -1,4 +1,5 @@
-// All-gather of the index streams over NVLink peer memory by the copy engines (included by nat_b200.cu).
+// All-gather of the index streams over NVLink peer memory by the copy engines. Host code only, its own translation
+// unit (csrc/ holds the kernel sources and their launcher: the sources bench.build_id ties the ncu captures to).
 //
 // One process per GPU. Every rank owns two output buffers [rows, world * cols] (double buffered by step) and one step
 // counter per sender, all plain device memory exported through CUDA IPC. A step, on the caller's stream:
@@ -10,6 +11,45 @@
 // No kernel runs: NCCL's all-gather kernel has to squeeze in beside a persistent kernel that owns every SM, these
 // copies do not touch an SM. A sender is at most one step ahead of the slowest receiver (it cannot pass step s + 1's
 // wait before every rank has sent s + 1, i.e. has finished consuming s on the same stream), so two buffers suffice.
+// Teardown is two-phase: every rank unmaps its peers' buffers (nat_peer_disconnect), the ranks meet at a barrier of
+// the caller's, and only then does anyone free the memory the others had mapped (nat_peer_destroy): freeing an
+// exported allocation that an importer still maps is undefined.
+#include "../../include/nat_b200.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_peer_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_peer_error = buf;
+    return code;
+}
+
+#define NAT_CUDA(expr)                                                                                        \
+    do {                                                                                                      \
+        cudaError_t e__ = (expr);                                                                             \
+        if (e__ != cudaSuccess)                                                                               \
+            return fail(NAT_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+}  // namespace
+
+const char* nat_peer_last_error(void) { return g_peer_error.c_str(); }
+
 struct nat_peer_ctx {
     int world = 0, rank = 0, device = 0;
     size_t rows = 0, col_bytes = 0, pitch = 0;      // block: rows x col_bytes; output row pitch = world * col_bytes
@@ -120,13 +160,24 @@ void* nat_peer_buffer(const nat_peer_ctx* ctx, int which) {
     return ctx == nullptr ? nullptr : ctx->out + static_cast<size_t>(which & 1) * ctx->rows * ctx->pitch;
 }
 
-void nat_peer_destroy(nat_peer_ctx* ctx) {
-    if (ctx == nullptr) return;
+int nat_peer_disconnect(nat_peer_ctx* ctx) {
+    if (ctx == nullptr) return fail(NAT_ERR_INVALID_ARGUMENT, "null argument");
+    cudaError_t first = cudaSuccess;
     for (int p = 0; p < ctx->world; ++p) {
         if (p == ctx->rank) continue;
-        if (ctx->peer_out[p] != nullptr) cudaIpcCloseMemHandle(ctx->peer_out[p]);
-        if (ctx->peer_flags[p] != nullptr) cudaIpcCloseMemHandle(ctx->peer_flags[p]);
+        if (ctx->peer_out[p] != nullptr) { const cudaError_t e = cudaIpcCloseMemHandle(ctx->peer_out[p]); if (first == cudaSuccess) first = e; }
+        if (ctx->peer_flags[p] != nullptr) { const cudaError_t e = cudaIpcCloseMemHandle(ctx->peer_flags[p]); if (first == cudaSuccess) first = e; }
+        ctx->peer_out[p] = nullptr;
+        ctx->peer_flags[p] = nullptr;
     }
+    ctx->connected = ctx->world == 1;
+    if (first != cudaSuccess) return fail(NAT_ERR_CUDA, "cudaIpcCloseMemHandle failed: %s", cudaGetErrorString(first));
+    return NAT_OK;
+}
+
+void nat_peer_destroy(nat_peer_ctx* ctx) {
+    if (ctx == nullptr) return;
+    nat_peer_disconnect(ctx);            // a no-op after an explicit disconnect
     cudaFree(ctx->out); cudaFree(ctx->flags); cudaFree(ctx->step_word);
     delete ctx;
 }

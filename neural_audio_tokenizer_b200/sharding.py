@@ -141,17 +141,39 @@ class PeerCodeGatherer:
                                "runs on any torch.distributed backend)")
         import ctypes
         self._ctx = ctypes.c_void_p()
+        # Set-up is collective: a rank that fails locally still takes part in every exchange below, and all ranks
+        # agree on the outcome before anyone returns (or raises), so a caller can fall back to CodeGatherer everywhere.
+        err = None
         with torch.cuda.device(self.device):
-            _lib.check(lib.nat_peer_create(world, self.rank, n_layers, self.per * 2, ctypes.byref(self._ctx)))
             mine = (ctypes.c_ubyte * _lib.PEER_HANDLE_BYTES)()
-            _lib.check(lib.nat_peer_export(self._ctx, mine))
+            try:
+                _lib.check_peer(lib.nat_peer_create(world, self.rank, n_layers, self.per * 2, ctypes.byref(self._ctx)))
+                _lib.check_peer(lib.nat_peer_export(self._ctx, mine))
+            except Exception as e:                              # noqa: BLE001 - reported after the agreement
+                err = e
             if world > 1:
                 send = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(self.device)
                 recv = torch.empty(world * _lib.PEER_HANDLE_BYTES, dtype=torch.uint8, device=self.device)
                 dist.all_gather_into_tensor(recv, send, group=group)
-                blob = bytes(recv.cpu().numpy().tobytes())
-                _lib.check(lib.nat_peer_connect(self._ctx, ctypes.c_char_p(blob)))
-                dist.barrier(group=group)                       # every rank has opened every buffer before the first push
+                if err is None:
+                    try:
+                        blob = bytes(recv.cpu().numpy().tobytes())
+                        _lib.check_peer(lib.nat_peer_connect(self._ctx, ctypes.c_char_p(blob)))
+                    except Exception as e:                      # noqa: BLE001
+                        err = e
+                self._agree(err, "set-up")                      # also: every rank has opened every buffer
+                # one empty exchange proves the stream memory operations work here before a caller relies on them
+                try:
+                    probe = torch.zeros((n_layers, self.per), dtype=torch.int16, device=self.device)
+                    got = ctypes.c_void_p()
+                    _lib.check_peer(lib.nat_peer_all_gather(self._ctx, probe.data_ptr(), self.per * 2,
+                                                       torch.cuda.current_stream(self.device).cuda_stream, ctypes.byref(got)))
+                    torch.cuda.synchronize(self.device)
+                except Exception as e:                          # noqa: BLE001
+                    err = e
+                self._agree(err, "first exchange")
+            elif err is not None:
+                raise err
         self.out = [torch.as_tensor(_DeviceArray(lib.nat_peer_buffer(self._ctx, k), (n_layers, world * self.per), "<i2", self),
                                     device=self.device) for k in range(2)]
         self.comm = torch.cuda.Stream(device=self.device)
@@ -159,7 +181,17 @@ class PeerCodeGatherer:
         self.staged = [torch.cuda.Event() for _ in range(2)]
         self.done = [torch.cuda.Event() for _ in range(2)]
         self.used = [False, False]
-        self.i = 0
+        self.i = 1 if world > 1 else 0                          # the probe exchange was the library's step 1
+
+    def _agree(self, err, what: str) -> None:
+        flag = torch.tensor([0 if err is None else 1], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+        if int(flag.item()) != 0:
+            if self._ctx:
+                self._lib_mod.load().nat_peer_destroy(self._ctx)
+                self._ctx = None
+            raise RuntimeError(f"peer-memory exchange unavailable ({what}) on at least one rank"
+                               + (f"; this rank: {err}" if err is not None else ""))
 
     def all_gather(self, local_codes: torch.Tensor) -> torch.Tensor:
         import ctypes
@@ -176,7 +208,7 @@ class PeerCodeGatherer:
         self.comm.wait_event(self.staged[k])
         got = ctypes.c_void_p()
         with torch.cuda.device(self.device):
-            self._lib_mod.check(lib.nat_peer_all_gather(self._ctx, self.send[k].data_ptr(), self.per * 2,
+            self._lib_mod.check_peer(lib.nat_peer_all_gather(self._ctx, self.send[k].data_ptr(), self.per * 2,
                                                         self.comm.cuda_stream, ctypes.byref(got)))
         assert got.value == self.out[k].data_ptr()
         self.done[k].record(self.comm)
@@ -190,9 +222,17 @@ class PeerCodeGatherer:
                 cur.wait_event(self.done[k])
 
     def close(self) -> None:
+        """Collective. Two-phase: everybody stops writing, everybody unmaps the peers' buffers, and only then does
+        anyone free memory the others had mapped (freeing an exported allocation an importer still maps is undefined;
+        the first version of this method freed right after one barrier and hung torchrun jobs at exit)."""
         if self._ctx:
+            lib = self._lib_mod.load()
+            multi = dist.is_initialized() and self.world > 1
             torch.cuda.synchronize(self.device)
-            if dist.is_initialized() and self.world > 1:
-                dist.barrier(group=self.group)                  # nobody unmaps a buffer a peer may still write
-            self._lib_mod.load().nat_peer_destroy(self._ctx)
+            if multi:
+                dist.barrier(group=self.group)                  # no rank still pushes into anybody's buffers
+            lib.nat_peer_disconnect(self._ctx)
+            if multi:
+                dist.barrier(group=self.group)                  # no rank still maps anybody's buffers
+            lib.nat_peer_destroy(self._ctx)
             self._ctx = None
