@@ -296,7 +296,7 @@ int nat_debug_rvq_scores(const nat_rvq_codebooks* cb, int layer, const float* ro
 int nat_debug_stack_counters(nat_rvq_codebooks* cb, int enable, unsigned long long* out_host, int max_ctas,
                              int* n_ctas, int* n_slots);
 
-/* ---- all-gather of the index streams over NVLink peer memory (one process per GPU; csrc/peer_exchange.inc) ----------
+/* ---- all-gather of the index streams over NVLink peer memory (one process per GPU; csrc_host/peer_exchange.cpp) ----------
  * Replaces the `dist.all_gather` a sharded run would issue on the [L, frames] index streams (the
  * reference itself is single-device). Every rank's [rows, col_bytes] block is written by the copy engines straight
  * into its column range of every rank's [rows, world * col_bytes] output; no kernel, no staging on the receiver.

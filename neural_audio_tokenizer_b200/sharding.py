@@ -118,7 +118,7 @@ class _DeviceArray:
 class PeerCodeGatherer:
     """`CodeGatherer` without a collective kernel: every rank's [L, n_local] index streams are written by the copy
     engines over NVLink straight into their column range of every rank's [L, world * per] output
-    (nat_peer_all_gather, csrc/peer_exchange.inc). No SM is involved, so the exchange does not compete with the
+    (nat_peer_all_gather, csrc_host/peer_exchange.cpp). No SM is involved, so the exchange does not compete with the
     persistent stack kernel of the next step the way NCCL's all-gather kernel does. One process per GPU on one box
     (CUDA IPC); torch.distributed is used once, to pass the IPC handles around.
 
@@ -187,8 +187,12 @@ class PeerCodeGatherer:
         flag = torch.tensor([0 if err is None else 1], dtype=torch.int32, device=self.device)
         dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
         if int(flag.item()) != 0:
+            lib = self._lib_mod.load()
             if self._ctx:
-                self._lib_mod.load().nat_peer_destroy(self._ctx)
+                lib.nat_peer_disconnect(self._ctx)
+            dist.barrier(group=self.group)                      # nobody maps anybody's buffers any more
+            if self._ctx:
+                lib.nat_peer_destroy(self._ctx)
                 self._ctx = None
             raise RuntimeError(f"peer-memory exchange unavailable ({what}) on at least one rank"
                                + (f"; this rank: {err}" if err is not None else ""))

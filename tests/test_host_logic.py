@@ -161,3 +161,11 @@ def test_shard_range_partitions_exactly():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(e - s for s, e in spans) == -(-n // world)
     assert list(shard_clips(10, 4, 1)) == [1, 5, 9]
+
+
+def test_peer_gatherer_needs_cuda_devices():
+    """The copy-engine exchange moves device memory over NVLink: on a host device it refuses loudly (CodeGatherer is the
+    form that runs on any torch.distributed backend), it does not fall back."""
+    from neural_audio_tokenizer_b200.sharding import PeerCodeGatherer
+    with pytest.raises(RuntimeError, match="CUDA"):
+        PeerCodeGatherer(8, 100, 1, "cpu")

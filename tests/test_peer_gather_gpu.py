@@ -1,4 +1,4 @@
-"""All-gather of the index streams over NVLink peer memory (sharding.PeerCodeGatherer, csrc/peer_exchange.inc) on two
+"""All-gather of the index streams over NVLink peer memory (sharding.PeerCodeGatherer, csrc_host/peer_exchange.cpp) on two
 GPUs, one process each: equal to torch.distributed's all-gather of the same blocks over many steps, ragged totals
 included. Skipped on a box with one GPU (the driver's GPU test box; run with `gpurun --gpus 2`)."""
 import os
