@@ -300,7 +300,8 @@ int nat_debug_stack_counters(nat_rvq_codebooks* cb, int enable, unsigned long lo
  * Replaces the `dist.all_gather` a sharded run would issue on the [L, frames] index streams (the
  * reference itself is single-device). Every rank's [rows, col_bytes] block is written by the copy engines straight
  * into its column range of every rank's [rows, world * col_bytes] output; no kernel, no staging on the receiver.
- *   nat_peer_create      allocates this rank's two output buffers and step counters on the current device
+ *   nat_peer_create      allocates this rank's three output buffers (step s uses buffer s % 3) and step counters on the
+ *                        current device
  *   nat_peer_export      writes two CUDA IPC handles (128 bytes) to hand to the other ranks (any transport)
  *   nat_peer_connect     handles_all = the world's 128-byte records in rank order
  *   nat_peer_all_gather  stream-ordered: pushes `block_dev` (row pitch `block_pitch` bytes) to every rank, then makes

@@ -1,7 +1,7 @@
 // All-gather of the index streams over NVLink peer memory by the copy engines. Host code only, its own translation
 // unit (csrc/ holds the kernel sources and their launcher: the sources bench.build_id ties the ncu captures to).
 //
-// One process per GPU. Every rank owns two output buffers [rows, world * cols] (double buffered by step) and one step
+// One process per GPU. Every rank owns three output buffers [rows, world * cols] (step s uses buffer s % 3) and one step
 // counter per sender, all plain device memory exported through CUDA IPC. A step, on the caller's stream:
 //   1. one 2-D peer copy per rank writes this rank's [rows, cols] block straight into its column range of every
 //      rank's output buffer (the final layout: no staging on the receiver, no un-pad or permute kernel);
@@ -9,8 +9,10 @@
 //   3. the stream waits (cuStreamWaitValue32, flushing remote writes) until every sender's counter has reached the
 //      step.
 // No kernel runs: NCCL's all-gather kernel has to squeeze in beside a persistent kernel that owns every SM, these
-// copies do not touch an SM. A sender is at most one step ahead of the slowest receiver (it cannot pass step s + 1's
-// wait before every rank has sent s + 1, i.e. has finished consuming s on the same stream), so two buffers suffice.
+// copies do not touch an SM. A sender can start step s + 2 as soon as every rank has SENT step s + 1, which a receiver
+// that consumes its results one step late (the overlapped use) does before it has read step s: with two buffers the
+// remote writes of s + 2 would land on the buffer it is still reading. With three, buffer s % 3 is written again by
+// step s + 3, which needs every rank's step s + 2 call; a result is therefore valid until the call after next.
 // Teardown is two-phase: every rank unmaps its peers' buffers (nat_peer_disconnect), the ranks meet at a barrier of
 // the caller's, and only then does anyone free the memory the others had mapped (nat_peer_destroy): freeing an
 // exported allocation that an importer still maps is undefined.
@@ -50,10 +52,12 @@ int fail(int code, const char* fmt, ...) {
 
 const char* nat_peer_last_error(void) { return g_peer_error.c_str(); }
 
+constexpr unsigned kPeerBuffers = 3;
+
 struct nat_peer_ctx {
     int world = 0, rank = 0, device = 0;
     size_t rows = 0, col_bytes = 0, pitch = 0;      // block: rows x col_bytes; output row pitch = world * col_bytes
-    char* out = nullptr;                            // [2][rows][pitch]
+    char* out = nullptr;                            // [kPeerBuffers][rows][pitch]
     uint32_t* flags = nullptr;                      // [world] step counters written by the senders
     uint32_t* step_word = nullptr;                  // the value this rank sends
     std::vector<char*> peer_out;
@@ -87,7 +91,7 @@ int nat_peer_create(int world, int rank, size_t rows, size_t col_bytes, nat_peer
     ctx->peer_out.assign(world, nullptr); ctx->peer_flags.assign(world, nullptr);
     auto cleanup = [&](int rc) { cudaFree(ctx->out); cudaFree(ctx->flags); cudaFree(ctx->step_word); delete ctx; return rc; };
     if (cudaGetDevice(&ctx->device) != cudaSuccess) return cleanup(fail(NAT_ERR_CUDA, "cudaGetDevice failed"));
-    const size_t bytes = 2 * rows * ctx->pitch;
+    const size_t bytes = kPeerBuffers * rows * ctx->pitch;
     if (cudaMalloc(&ctx->out, bytes) != cudaSuccess || cudaMalloc(&ctx->flags, sizeof(uint32_t) * world) != cudaSuccess ||
         cudaMalloc(&ctx->step_word, sizeof(uint32_t)) != cudaSuccess)
         return cleanup(fail(NAT_ERR_CUDA, "cudaMalloc of the exchange buffers failed: %s", cudaGetErrorString(cudaGetLastError())));
@@ -132,7 +136,7 @@ int nat_peer_all_gather(nat_peer_ctx* ctx, const void* block_dev, size_t block_p
     if (block_pitch < ctx->col_bytes) return fail(NAT_ERR_INVALID_ARGUMENT, "block pitch smaller than a row of the block");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const unsigned s = ++ctx->step;
-    const size_t buf = static_cast<size_t>(s & 1u) * ctx->rows * ctx->pitch;
+    const size_t buf = static_cast<size_t>(s % kPeerBuffers) * ctx->rows * ctx->pitch;
     for (int i = 0; i < ctx->world; ++i) {
         const int p = (ctx->rank + i) % ctx->world;                 // every rank starts with a different receiver
         NAT_CUDA(cudaMemcpy2DAsync(ctx->peer_out[p] + buf + ctx->rank * ctx->col_bytes, ctx->pitch, block_dev, block_pitch,
@@ -157,7 +161,7 @@ int nat_peer_all_gather(nat_peer_ctx* ctx, const void* block_dev, size_t block_p
 }
 
 void* nat_peer_buffer(const nat_peer_ctx* ctx, int which) {
-    return ctx == nullptr ? nullptr : ctx->out + static_cast<size_t>(which & 1) * ctx->rows * ctx->pitch;
+    return ctx == nullptr ? nullptr : ctx->out + static_cast<size_t>(static_cast<unsigned>(which) % kPeerBuffers) * ctx->rows * ctx->pitch;
 }
 
 int nat_peer_disconnect(nat_peer_ctx* ctx) {

@@ -124,7 +124,8 @@ class PeerCodeGatherer:
 
     Same interface as CodeGatherer: `all_gather(local)` stages the rank's streams on the caller's stream, runs the
     exchange on a side stream and returns the output tensor of this step, valid after `wait()` (or in the side
-    stream's order); outputs are double buffered."""
+    stream's order) and until the call after next (three output buffers: a peer may start writing step s + 2 while
+    this rank still reads step s)."""
 
     def __init__(self, n_layers: int, n_local: int, world: int, device, n_total: int = None, group=None):
         from . import _lib
@@ -175,7 +176,7 @@ class PeerCodeGatherer:
             elif err is not None:
                 raise err
         self.out = [torch.as_tensor(_DeviceArray(lib.nat_peer_buffer(self._ctx, k), (n_layers, world * self.per), "<i2", self),
-                                    device=self.device) for k in range(2)]
+                                    device=self.device) for k in range(3)]
         self.comm = torch.cuda.Stream(device=self.device)
         self.send = [torch.zeros((n_layers, self.per), dtype=torch.int16, device=self.device) for _ in range(2)]
         self.staged = [torch.cuda.Event() for _ in range(2)]
@@ -203,7 +204,8 @@ class PeerCodeGatherer:
             raise ValueError(f"expected [{self.L}, {self.n_local}] index streams, got {tuple(local_codes.shape)}")
         lib = self._lib_mod.load()
         self.i += 1
-        k = self.i & 1                                          # the library's buffer of step i is buffer i & 1
+        k = self.i & 1                                          # staging buffers alternate
+        kb = self.i % 3                                         # the library's output buffer of step i
         cur = torch.cuda.current_stream(self.device)
         if self.used[k]:
             cur.wait_event(self.done[k])                        # the staging buffer's previous exchange has been sent
@@ -214,10 +216,10 @@ class PeerCodeGatherer:
         with torch.cuda.device(self.device):
             self._lib_mod.check_peer(lib.nat_peer_all_gather(self._ctx, self.send[k].data_ptr(), self.per * 2,
                                                         self.comm.cuda_stream, ctypes.byref(got)))
-        assert got.value == self.out[k].data_ptr()
+        assert got.value == self.out[kb].data_ptr()
         self.done[k].record(self.comm)
         self.used[k] = True
-        return self.out[k][:, :self.n_total] if self.world * self.per != self.n_total else self.out[k]
+        return self.out[kb][:, :self.n_total] if self.world * self.per != self.n_total else self.out[kb]
 
     def wait(self) -> None:
         cur = torch.cuda.current_stream(self.device)
