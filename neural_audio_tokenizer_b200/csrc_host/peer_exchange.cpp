@@ -92,7 +92,11 @@ int nat_peer_create(int world, int rank, size_t rows, size_t col_bytes, nat_peer
     auto cleanup = [&](int rc) { cudaFree(ctx->out); cudaFree(ctx->flags); cudaFree(ctx->step_word); delete ctx; return rc; };
     if (cudaGetDevice(&ctx->device) != cudaSuccess) return cleanup(fail(NAT_ERR_CUDA, "cudaGetDevice failed"));
     const size_t bytes = kPeerBuffers * rows * ctx->pitch;
-    if (cudaMalloc(&ctx->out, bytes) != cudaSuccess || cudaMalloc(&ctx->flags, sizeof(uint32_t) * world) != cudaSuccess ||
+    // An IPC handle exports the whole allocation block a pointer lives in: both exported buffers get blocks of their
+    // own (sizes rounded up to 2 MiB), so no unrelated small allocation of this process shares a block with them.
+    constexpr size_t kIpcGranule = size_t(2) << 20;
+    const size_t out_alloc = (bytes + kIpcGranule - 1) / kIpcGranule * kIpcGranule;
+    if (cudaMalloc(&ctx->out, out_alloc) != cudaSuccess || cudaMalloc(&ctx->flags, kIpcGranule) != cudaSuccess ||
         cudaMalloc(&ctx->step_word, sizeof(uint32_t)) != cudaSuccess)
         return cleanup(fail(NAT_ERR_CUDA, "cudaMalloc of the exchange buffers failed: %s", cudaGetErrorString(cudaGetLastError())));
     if (cudaMemset(ctx->out, 0, bytes) != cudaSuccess || cudaMemset(ctx->flags, 0, sizeof(uint32_t) * world) != cudaSuccess)
